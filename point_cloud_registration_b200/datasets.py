@@ -1,0 +1,154 @@
+"""Workload generators and a minimal PCD reader (host side, NumPy only).
+
+The reference benchmarks on ``data/B-01.pcd`` through ``benchmark/test_data.py:21-44``
+(scan = rigidly moved, noised copy of the map).  That file cannot travel to the GPU box,
+so the bench/test workloads are synthetic scenes with the same character (SURVEY.md
+section 8d): 2-D surfaces embedded in 3-D at B-01's surface density (~170 pts/m^2) so that
+kNN normals and voxel planes are meaningful and occupied 0.5 m voxels hold >= 10 points.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+B01_POINTS = 1_193_011            # size of the reference's data/B-01.pcd
+SURFACE_DENSITY = 170.0           # points / m^2 measured on B-01
+
+
+def rodrigues(w):
+    """Plain Rodrigues rotation (always orthonormal) used only to build test scenes."""
+    w = np.asarray(w, dtype=np.float64)
+    th = np.linalg.norm(w)
+    if th < 1e-12:
+        return np.eye(3)
+    k = w / th
+    K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def make_urban_slab(n_points, seed=0, density=SURFACE_DENSITY, dtype=np.float32):
+    """Synthetic "urban slab": undulating ground + randomly oriented vertical wall patches
+    + box clutter, sampled uniformly at ``density`` points per square metre with 1 cm
+    roughness.  Deterministic in (n_points, seed).  Returns (n_points, 3) ``dtype``."""
+    rng = np.random.default_rng(seed)
+    n = int(n_points)
+    area = n / density
+    n_ground = int(round(0.50 * n))
+    n_wall = int(round(0.35 * n))
+    n_box = n - n_ground - n_wall
+    side = np.sqrt(0.50 * area)
+    half = 0.5 * side
+
+    def ground_z(x, y):
+        return 0.30 * np.sin(x / 15.0) * np.cos(y / 11.0)
+
+    out = np.empty((n, 3), dtype=np.float64)
+
+    # ground
+    gx = rng.uniform(-half, half, n_ground)
+    gy = rng.uniform(-half, half, n_ground)
+    out[:n_ground, 0], out[:n_ground, 1], out[:n_ground, 2] = gx, gy, ground_z(gx, gy)
+
+    # walls: vertical rectangles, random yaw / size / position
+    wall_area = 0.35 * area
+    n_walls = max(8, int(round(wall_area / 69.0)))
+    w_len = rng.uniform(5.0, 20.0, n_walls)
+    w_hgt = rng.uniform(3.0, 8.0, n_walls)
+    w_yaw = rng.uniform(0.0, np.pi, n_walls)
+    w_cx = rng.uniform(-half, half, n_walls)
+    w_cy = rng.uniform(-half, half, n_walls)
+    cum = np.cumsum(w_len * w_hgt)
+    which = np.searchsorted(cum, rng.uniform(0.0, cum[-1], n_wall), side="right")
+    which = np.minimum(which, n_walls - 1)
+    u = (rng.uniform(-0.5, 0.5, n_wall)) * w_len[which]
+    v = rng.uniform(0.0, 1.0, n_wall) * w_hgt[which]
+    wx = w_cx[which] + u * np.cos(w_yaw[which])
+    wy = w_cy[which] + u * np.sin(w_yaw[which])
+    sl = slice(n_ground, n_ground + n_wall)
+    out[sl, 0], out[sl, 1], out[sl, 2] = wx, wy, ground_z(w_cx[which], w_cy[which]) + v
+
+    # box clutter: points on the five visible faces of small axis-aligned boxes
+    box_area = max(area - 0.50 * area - wall_area, 1.0)
+    n_boxes = max(4, int(round(box_area / 14.0)))
+    b_sz = rng.uniform(1.0, 3.0, (n_boxes, 3))
+    b_c = np.stack([rng.uniform(-half, half, n_boxes), rng.uniform(-half, half, n_boxes)], axis=1)
+    which = rng.integers(0, n_boxes, n_box)
+    face = rng.integers(0, 5, n_box)                     # 0:+x 1:-x 2:+y 3:-y 4:top
+    a = rng.uniform(-0.5, 0.5, n_box)
+    b = rng.uniform(0.0, 1.0, n_box)
+    sx, sy, sz = b_sz[which, 0], b_sz[which, 1], b_sz[which, 2]
+    lx = np.where(face == 0, 0.5, np.where(face == 1, -0.5, a)) * sx
+    ly = np.where(face == 2, 0.5, np.where(face == 3, -0.5, np.where(face == 4, rng.uniform(-0.5, 0.5, n_box), a))) * sy
+    lz = np.where(face == 4, 1.0, b) * sz
+    sl = slice(n_ground + n_wall, n)
+    out[sl, 0] = b_c[which, 0] + lx
+    out[sl, 1] = b_c[which, 1] + ly
+    out[sl, 2] = ground_z(b_c[which, 0], b_c[which, 1]) + lz
+
+    out += rng.normal(0.0, 0.01, out.shape)              # surface roughness
+    rng.shuffle(out, axis=0)                             # acquisition order is not spatial
+    return out.astype(dtype)
+
+
+def perturb_scan(target, so3=(0.01, -0.02, 0.03), t=(0.1, -0.2, 0.3), sigma=0.005, seed=0,
+                 num_points=None, dtype=np.float32):
+    """scan = R * target + t (+ N(0, sigma^2)), optionally a random subsample without
+    replacement -- the shape of the reference's ``generate_test_data``
+    (benchmark/test_data.py:21-44) with the section-8d perturbation as default."""
+    rng = np.random.default_rng(seed)
+    pts = np.asarray(target, dtype=np.float64)
+    if num_points is not None and num_points < pts.shape[0]:
+        pts = pts[rng.choice(pts.shape[0], int(num_points), replace=False)]
+    scan = pts @ rodrigues(so3).T + np.asarray(t, dtype=np.float64)
+    if sigma > 0:
+        scan = scan + rng.normal(0.0, sigma, scan.shape)
+    return scan.astype(dtype)
+
+
+def unit_cube_case(n=10000, scale=1.0, seed=42):
+    """The reference tests' fixture shape (tests/test_icp.py:7-17) at size ``n``:
+    target ~ U[0,1)^3 (float64), source = R target + t with so3 = scale*[.1,.2,.3],
+    t = scale*[.5,-.3,.2]; ``scale=1`` reproduces the reference fixture exactly when n=100."""
+    rs = np.random.RandomState(seed)
+    target = rs.rand(n, 3)
+    R = rodrigues(scale * np.array([0.1, 0.2, 0.3]))
+    t = scale * np.array([0.5, -0.3, 0.2])
+    source = (R @ target.T).T + t
+    return target, source
+
+
+def load_pcd_xyz(path):
+    """Minimal reader for binary/ascii PCD files with float32 x,y,z as the first three
+    fields (enough for the reference's data/B-01.pcd: 20-byte records
+    ``<f4 x,y,z; u4 intensity; u4 rgb``).  Returns (N,3) float32."""
+    with open(path, "rb") as fh:
+        fields, sizes, counts, npts, mode = [], [], [], None, None
+        while True:
+            line = fh.readline()
+            if not line:
+                raise ValueError("PCD header ended without DATA line")
+            tok = line.decode("ascii", "replace").strip().split()
+            if not tok or tok[0].startswith("#"):
+                continue
+            key = tok[0].upper()
+            if key == "FIELDS":
+                fields = tok[1:]
+            elif key == "SIZE":
+                sizes = [int(v) for v in tok[1:]]
+            elif key == "COUNT":
+                counts = [int(v) for v in tok[1:]]
+            elif key == "POINTS":
+                npts = int(tok[1])
+            elif key == "DATA":
+                mode = tok[1].lower()
+                break
+        if fields[:3] != ["x", "y", "z"] or sizes[:3] != [4, 4, 4]:
+            raise ValueError("unsupported PCD layout: need float32 x y z first")
+        if not counts:
+            counts = [1] * len(fields)
+        stride = sum(s * c for s, c in zip(sizes, counts))
+        if mode == "binary":
+            raw = np.frombuffer(fh.read(npts * stride), dtype=np.uint8).reshape(npts, stride)
+            return raw[:, :12].copy().view("<f4").reshape(npts, 3)
+        if mode == "ascii":
+            return np.loadtxt(fh, dtype=np.float32, usecols=(0, 1, 2)).reshape(-1, 3)
+        raise ValueError(f"unsupported PCD DATA mode {mode!r}")
