@@ -1,0 +1,176 @@
+/*
+ * pcr_b200.h -- C ABI of libpcr_b200.so: the B200 (sm_100a) implementation of the
+ * per-iteration hot path of scomup/point-cloud-registration and of its once-per-target
+ * builds.  Plain C symbols, plain pointers and sizes, no torch/numpy types.
+ *
+ * The reference has no FFI layer: its "operator API" is the Python class surface
+ * re-exported at point_cloud_registration/__init__.py:1-10.  Each entry point below names
+ * the reference interface it replaces (paths relative to
+ * /root/reference/point_cloud_registration/).  The Python classes in
+ * point_cloud_registration_b200/ bind these symbols with ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative PCR_ERR_* code; the message is
+ *     available from pcr_last_error(ctx) (ctx may be NULL for creation failures);
+ *   - the caller owns all host buffers; the library owns all device buffers;
+ *   - xyz inputs are C-contiguous (n,3) float32 unless stated; a pointer may be a HOST
+ *     pointer (pageable or pinned) or a CUDA DEVICE pointer -- the library checks with
+ *     cudaPointerGetAttributes and copies accordingly;
+ *   - one context = one GPU + one CUDA stream; calls on a context are serialised by the
+ *     caller; every entry point is synchronous with respect to its host outputs;
+ *   - 4x4 transforms are row-major float64; the state vector is dx = [dt(3), dtheta(3)]
+ *     with the right-multiplicative update of reference math_tools.py:101-108.
+ */
+#ifndef PCR_B200_H
+#define PCR_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcr_ctx pcr_ctx;
+
+#define PCR_OK 0
+#define PCR_ERR_CUDA (-1)      /* CUDA runtime failure (message carries the call)            */
+#define PCR_ERR_ARG (-2)       /* bad argument                                               */
+#define PCR_ERR_STATE (-3)     /* required structure not built (e.g. target not set)         */
+#define PCR_ERR_SINGULAR (-4)  /* singular normal equations (np.linalg.LinAlgError)          */
+#define PCR_ERR_NCCL (-5)      /* NCCL failure / library not found                           */
+#define PCR_ERR_LIMIT (-6)     /* structure would exceed the implementation's limits         */
+
+/* method ids for pcr_linearize / pcr_align */
+#define PCR_ICP 0     /* icp.py:24-57                 */
+#define PCR_PLANE 1   /* plane_icp.py:30-69           */
+#define PCR_VPLANE 2  /* voxelized_plane_icp.py:23-64 */
+#define PCR_NDT 3     /* ndt.py:24-57                 */
+
+/* Layout of the 29-double normal-equation record returned by pcr_linearize:
+ * [0..20] upper triangle of the 6x6 H, row major; [21..26] g; [27] e2; [28] inlier count. */
+#define PCR_RECORD_LEN 29
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int pcr_version(void);
+int pcr_device_count(int* count);
+int pcr_create(int device_id, pcr_ctx** out);
+int pcr_destroy(pcr_ctx* ctx);
+const char* pcr_last_error(const pcr_ctx* ctx);
+
+/* ---- target side (set_target) -------------------------------------------------------- */
+
+/* Upload the target cloud.  Replaces `self.target = target.astype(np.float32)`
+ * (icp.py:17-22, plane_icp.py:19-20). */
+int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n);
+
+/* Build the exact nearest-neighbour index over the target points.  Replaces
+ * `KDTree(target)` (kdtree.py:18-25 -> pykdtree; icp.py:20, plane_icp.py:22). */
+int pcr_build_nn_index(pcr_ctx* ctx);
+
+/* k-NN normal estimation on the device; k includes the point itself; float32 moment
+ * formula of the reference replayed (quirk Q5).  Replaces estimate_norm_with_tree
+ * (estimate_normals.py:27-87) as called from plane_icp.py:23-24. */
+int pcr_estimate_normals(pcr_ctx* ctx, int k);
+
+/* Inject / read back per-target-point normals, (n,3) float32, caller's point order.
+ * Injection mirrors `PlaneICP.set_target(target, kdree, norm)` (plane_icp.py:25-27). */
+int pcr_set_normals(pcr_ctx* ctx, const float* normals);
+int pcr_get_normals(pcr_ctx* ctx, float* normals);
+
+/* Voxel statistics of a cloud: group by floor(p / voxel_size), per-voxel mean, two-pass
+ * sample covariance, drop voxels with fewer than min_points points, plane normal =
+ * eigenvector of the smallest eigenvalue, optional closed-form inverse covariance, NN index
+ * over the kept means.  `xyz` is (n,3) float32 (is_f64 = 0) or float64 (is_f64 = 1); the
+ * statistics are accumulated in float64 exactly as the reference does for either dtype.
+ * Replaces VoxelGrid.set_points (voxel.py:104-165) and calc_icov (voxel.py:69-102) as
+ * called from voxelized_plane_icp.py:18-21 and ndt.py:18-22. */
+int pcr_build_voxels(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size,
+                     int min_points, int with_icov);
+
+/* Number of kept voxels and of occupied voxels before the min_points filter. */
+int pcr_get_voxel_count(pcr_ctx* ctx, int64_t* n_kept, int64_t* n_occupied);
+
+/* Read back kept-voxel attributes (any pointer may be NULL): mean (n,3), cov (n,3,3),
+ * norm (n,3), icov (n,3,3) float64, count (n) int64.  Voxel order = the library's own
+ * (brick-major); the reference's order (ascending hash key, voxel.py:109) is not part of
+ * its API.  Mirrors the attributes VoxelGrid.mean/.cov/.norm/.icov (voxel.py:160-164). */
+int pcr_get_voxels(pcr_ctx* ctx, double* mean, double* cov, double* norm, double* icov, int64_t* count);
+
+/* ---- scan side ------------------------------------------------------------------------- */
+
+/* Upload the scan once per align().  `sort` != 0 re-orders it along a Morton curve on the
+ * device (better cache behaviour of the correspondence search; the sums are order
+ * independent up to float64 rounding).  Replaces `source.astype(np.float32)`
+ * (registration.py:83). */
+int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort);
+
+/* ---- per iteration --------------------------------------------------------------------- */
+
+/* One linearisation at transform T: SE(3) transform of the scan, exact correspondence
+ * search, residual + Jacobian, reduction to the normal equations -- one fused kernel.
+ * Replaces ICP/PlaneICP/VPlaneICP/NDT.calc_H_g_e2 (icp.py:24, plane_icp.py:30,
+ * voxelized_plane_icp.py:23, ndt.py:24).  With a communicator attached (pcr_comm_init_rank)
+ * the record is summed over all ranks before it is returned. */
+int pcr_linearize(pcr_ctx* ctx, int method, const double T[16], double max_dist, double out[PCR_RECORD_LEN]);
+
+/* Whole Gauss-Newton solve on the device: linearise, 6x6 solve, stop test BEFORE the update
+ * (quirk Q8), T <- T [+] dx, without a host round trip per iteration.  Replaces
+ * Registration.align (registration.py:71-113).  `e2_trace` (may be NULL) receives the squared
+ * error of each executed linearisation (at most max_iter values); `iters` their number.
+ * Returns PCR_ERR_SINGULAR if a singular H was met (T_out = last transform). */
+int pcr_align(pcr_ctx* ctx, int method, const double T0[16], int max_iter, double tol, double max_dist,
+              double T_out[16], int* iters, double* e2_trace);
+
+/* The same loop, piecewise and asynchronous (used by pcr_align itself and by the benchmark to
+ * time single iterations with CUDA events on pcr_stream): begin resets the device loop state
+ * to T0; step_async enqueues `reps` fused iterations without synchronising (iterations after
+ * convergence are no-ops); state synchronises and reads the loop state back (`done`: 0 running,
+ * 1 converged, 2 singular, 3 max_iter reached). */
+int pcr_loop_begin(pcr_ctx* ctx, const double T0[16]);
+int pcr_loop_step_async(pcr_ctx* ctx, int method, int max_iter, double tol, double max_dist, int reps);
+int pcr_loop_state(pcr_ctx* ctx, double T_out[16], int* iters, int* done, double* e2_trace, int trace_cap);
+
+/* ---- utilities with reference-visible semantics --------------------------------------- */
+
+/* Exact k-NN of m query points against the target points: Euclidean distances (m,k)
+ * ascending, indices into the caller's target order; slots beyond the number of target
+ * points get dist = inf, idx = n.  Replaces KDTree.query (kdtree.py:18-25). */
+int pcr_knn(pcr_ctx* ctx, const float* queries, int64_t m, int k, float* dist, int64_t* idx);
+
+/* Nearest kept voxel MEAN for each query (quirk Q2): voxel ordinal (into pcr_get_voxels
+ * order) and float64 distance.  Replaces VoxelGrid.query (voxel.py:171-179). */
+int pcr_voxel_query(pcr_ctx* ctx, const float* queries, int64_t m, int64_t* vidx, double* dist);
+
+/* Per-voxel centroid down-sampling (voxel.py:209-241): writes at most n centroids
+ * (float32) to `out` and their number to n_out.  Voxel order = library's own. */
+int pcr_voxel_filter(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size,
+                     float* out, int64_t* n_out);
+
+/* ---- multi-GPU (scan tile-sharded, target replicated) ----------- */
+
+/* 128-byte NCCL unique id, created on rank 0 and shipped to the other ranks by the caller. */
+int pcr_comm_unique_id(void* id128);
+/* Attach this context to a communicator of `nranks` processes (one GPU each).  After this
+ * pcr_linearize / pcr_align all-reduce the 29-double record (ncclSum, float64). */
+int pcr_comm_init_rank(pcr_ctx* ctx, int nranks, int rank, const void* id128);
+int pcr_comm_destroy(pcr_ctx* ctx);
+
+/* ---- instrumentation -------------------------------------------------------------------- */
+
+/* CUDA-event duration (ms) of the kernels launched by the last pcr_linearize / pcr_align. */
+int pcr_last_kernel_ms(pcr_ctx* ctx, float* ms);
+/* Total number of kernels launched by this context so far. */
+int pcr_launch_count(pcr_ctx* ctx, int64_t* launches);
+/* Raw CUDA stream of the context (cudaStream_t as void*) for callers that time with events. */
+int pcr_stream(pcr_ctx* ctx, void** stream);
+/* Enqueue `reps` linearisations back to back WITHOUT host synchronisation (benchmark aid:
+ * lets the caller bracket them with its own CUDA events on pcr_stream). */
+int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max_dist, int reps);
+/* Grid statistics of the NN indices (cells, bricks, cell edge) for diagnostics. */
+int pcr_index_stats(pcr_ctx* ctx, int which /*0 target, 1 voxel*/, double* cell_edge, int64_t* n_cells,
+                    int64_t* n_bricks, int64_t* n_points);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCR_B200_H */

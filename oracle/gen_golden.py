@@ -89,6 +89,8 @@ def gen_ref_fixture():
                      ("NDT", dict(voxel_size=1.0))):
         o = make(name, max_iter=10, max_dist=2.0, tol=1e-3, **kw)
         o.set_target(target)
+        if name == "PlaneICP":
+            out["PlaneICP_normals"] = np.array(o.normal)
         H, g, e2 = o.calc_H_g_e2(np.eye(4), source)
         H2, g2, e22 = o.calc_H_g_e2_no_parallel_ver(np.eye(4), source)
         out[f"{name}_H"], out[f"{name}_g"], out[f"{name}_e2"] = H, g, e2

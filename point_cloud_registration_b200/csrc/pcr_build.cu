@@ -1,0 +1,927 @@
+// Once-per-target builds and query utilities of libpcr_b200.so (sm_100a):
+//   * brick-grid NN index over a point set            (replaces pykdtree KDTree(data), kdtree.py:18-25)
+//   * k-NN normals with the reference's float32 moments (estimate_normals.py:27-87)
+//   * voxel statistics / inverse covariance / voxel NN index (voxel.py:69-179)
+//   * k-NN and nearest-voxel queries, voxel_filter      (kdtree.py:18-25, voxel.py:171-179, 209-241)
+// Sorting / prefix sums use CUB (plumbing); every geometric kernel is hand written.
+#include <cub/cub.cuh>
+#include <cfloat>
+#include <climits>
+#include <vector>
+
+#include "pcr_context.cuh"
+#include "pcr_grid.cuh"
+#include "pcr_linalg.cuh"
+
+namespace pcr {
+
+static thread_local std::string g_err;
+void set_global_error(const std::string& s) { g_err = s; }
+const char* global_error() { return g_err.c_str(); }
+
+struct BrickRec {
+    unsigned long long mask;
+    uint32_t base;
+    uint32_t pad;
+};
+static_assert(sizeof(BrickRec) == 16, "brick record must be 16 bytes");
+
+__device__ __forceinline__ int f2ord(float f) {
+    int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+static inline float ord2f_host(int i) {
+    int j = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &j, 4);
+    return f;
+}
+
+// ---------------------------------------------------------------------------------------
+// bounding box of finite points: mm[0..2] = min (ordered ints), mm[3..5] = max
+// ---------------------------------------------------------------------------------------
+__global__ void bbox_kernel(const float* __restrict__ xyz, long long n, int* __restrict__ mm) {
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
+        if (isfinite(x) && isfinite(y) && isfinite(z)) {
+            int a = f2ord(x), b = f2ord(y), c = f2ord(z);
+            lo[0] = min(lo[0], a); hi[0] = max(hi[0], a);
+            lo[1] = min(lo[1], b); hi[1] = max(hi[1], b);
+            lo[2] = min(lo[2], c); hi[2] = max(hi[2], c);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&mm[a], lo[a]);
+            atomicMax(&mm[3 + a], hi[a]);
+        }
+    }
+}
+
+__global__ void init_minmax_kernel(int* mm) {
+    if (threadIdx.x < 3) mm[threadIdx.x] = INT_MAX;
+    else if (threadIdx.x < 6) mm[threadIdx.x] = INT_MIN;
+}
+
+// ---------------------------------------------------------------------------------------
+// point grid: keys, heads, fill, gather
+// ---------------------------------------------------------------------------------------
+__global__ void point_key_kernel(const float* __restrict__ xyz, long long n, GridView G,
+                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float big = 1.0e9f;
+    float gx = (xyz[3 * i] - G.ox) * G.inv_h, gy = (xyz[3 * i + 1] - G.oy) * G.inv_h, gz = (xyz[3 * i + 2] - G.oz) * G.inv_h;
+    if (!(gx == gx)) gx = 0.f;
+    if (!(gy == gy)) gy = 0.f;
+    if (!(gz == gz)) gz = 0.f;
+    int cx = cell_of(fminf(fmaxf(gx, -big), big), G.cnx);
+    int cy = cell_of(fminf(fmaxf(gy, -big), big), G.cny);
+    int cz = cell_of(fminf(fmaxf(gz, -big), big), G.cnz);
+    unsigned long long brick = ((unsigned long long)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2);
+    keys[i] = brick * 64ull + (unsigned long long)brick_bit(cx, cy, cz);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void head_flag_kernel(const unsigned long long* __restrict__ keys, long long n, uint32_t* __restrict__ flags) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    flags[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+
+// For each segment head: cell_start[ordinal] = position; set the brick's mask bit; the first
+// head of a brick records the brick's base ordinal.
+__global__ void grid_fill_kernel(const unsigned long long* __restrict__ keys, const uint32_t* __restrict__ flags,
+                                 const uint32_t* __restrict__ ords, long long n, uint32_t n_cells,
+                                 BrickRec* __restrict__ bricks, uint32_t* __restrict__ cell_start) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i == 0) cell_start[n_cells] = (uint32_t)n;
+    if (i >= n || !flags[i]) return;
+    const unsigned long long key = keys[i];
+    const uint32_t ord = ords[i];
+    cell_start[ord] = (uint32_t)i;
+    const unsigned long long brick = key >> 6;
+    atomicOr(&bricks[brick].mask, 1ull << (key & 63ull));
+    if (i == 0 || (keys[i - 1] >> 6) != brick) bricks[brick].base = ord;
+}
+
+__global__ void gather_points_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ vals, long long n,
+                                     float4* __restrict__ pts) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = vals[i];
+    pts[i] = make_float4(xyz[3 * (size_t)j], xyz[3 * (size_t)j + 1], xyz[3 * (size_t)j + 2], __uint_as_float(j));
+}
+
+static inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
+
+static int bits_for(unsigned long long v) {   // number of bits needed to represent values < v
+    int b = 1;
+    while (b < 64 && (1ull << b) < v) ++b;
+    return b;
+}
+
+// Sort (key64, val32) pairs by key (stable LSD radix sort).
+static int sort_pairs64(pcr_ctx* ctx, unsigned long long* k_in, unsigned long long* k_out, uint32_t* v_in, uint32_t* v_out,
+                        long long n, int end_bit) {
+    size_t tmp = 0;
+    PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, n, 0, end_bit, ctx->stream));
+    PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+    PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, n, 0, end_bit, ctx->stream));
+    ctx->launches += 4;
+    return PCR_OK;
+}
+
+static int exclusive_sum_u32(pcr_ctx* ctx, const uint32_t* in, uint32_t* out, long long n) {
+    size_t tmp = 0;
+    PCR_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp, in, out, n, ctx->stream));
+    PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+    PCR_CUDA(cub::DeviceScan::ExclusiveSum(ctx->cub_tmp.p, tmp, in, out, n, ctx->stream));
+    ctx->launches += 2;
+    return PCR_OK;
+}
+
+// segment count = ords[n-1] + flags[n-1]
+static int read_segment_count(pcr_ctx* ctx, const uint32_t* flags, const uint32_t* ords, long long n, uint32_t* out) {
+    uint32_t a = 0, b = 0;
+    PCR_CUDA(cudaMemcpyAsync(&a, ords + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(&b, flags + (n - 1), 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = a + b;
+    return PCR_OK;
+}
+
+constexpr unsigned long long kMaxBricks = 1ull << 27;   // 2 GiB of brick records
+
+// Build a brick grid over n points (device float[3n]) with automatically chosen cell edge.
+int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, DevBuf* sorted_payload_out) {
+    if (n <= 0) return fail(ctx, PCR_ERR_ARG, "cannot index an empty point set");
+    if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "point count exceeds 2^31-1");
+    g.release();
+    // ---- bounding box ----
+    PCR_CUDA(ctx->tmp_e.ensure(64));
+    int* d_mm = ctx->tmp_e.as<int>();
+    init_minmax_kernel<<<1, 32, 0, ctx->stream>>>(d_mm);
+    PCR_LAUNCH_CHECK();
+    bbox_kernel<<<min(blocks_for(n, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(d_xyz, n, d_mm);
+    PCR_LAUNCH_CHECK();
+    int h_mm[6];
+    PCR_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_mm[0] == INT_MAX) return fail(ctx, PCR_ERR_ARG, "point set has no finite points");
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = ord2f_host(h_mm[a]); hi[a] = ord2f_host(h_mm[3 + a]); }
+    double ext[3], maxext = 0, maxabs = 0;
+    for (int a = 0; a < 3; ++a) {
+        ext[a] = (double)hi[a] - (double)lo[a];
+        maxext = std::max(maxext, ext[a]);
+        maxabs = std::max(maxabs, std::max(fabs((double)lo[a]), fabs((double)hi[a])));
+    }
+    if (maxext <= 0) maxext = 1.0;
+    double vol = 1.0;
+    for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * maxext);
+    double h = cbrt(vol * 6.0 / (double)n);
+    h = std::max(h, maxext * 1e-5);
+
+    PCR_CUDA(ctx->tmp_a.ensure((size_t)n * 8));
+    PCR_CUDA(ctx->tmp_b.ensure((size_t)n * 8));
+    PCR_CUDA(ctx->tmp_c.ensure((size_t)n * 4 * 2));
+    PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
+    unsigned long long* k_in = ctx->tmp_a.as<unsigned long long>();
+    unsigned long long* k_out = ctx->tmp_b.as<unsigned long long>();
+    uint32_t* v_in = ctx->tmp_c.as<uint32_t>();
+    uint32_t* v_out = v_in + n;
+    uint32_t* flags = ctx->tmp_d.as<uint32_t>();
+    uint32_t* ords = flags + n;
+
+    const int max_attempts = 4;
+    for (int attempt = 0; attempt < max_attempts; ++attempt) {
+        GridView V{};
+        unsigned long long nbricks;
+        for (;;) {   // enlarge h until the dense brick table fits
+            V.h = (float)h;
+            V.inv_h = (float)(1.0 / h);
+            V.ox = lo[0] - 0.25f * V.h; V.oy = lo[1] - 0.25f * V.h; V.oz = lo[2] - 0.25f * V.h;
+            double c[3];
+            for (int a = 0; a < 3; ++a) c[a] = floor(((double)hi[a] - (double)(lo[a] - 0.25f * V.h)) / h) + 2.0;
+            V.bnx = (int)std::min(c[0] / 4.0 + 1.0, 2.0e9); V.bny = (int)std::min(c[1] / 4.0 + 1.0, 2.0e9); V.bnz = (int)std::min(c[2] / 4.0 + 1.0, 2.0e9);
+            nbricks = (unsigned long long)V.bnx * V.bny * V.bnz;
+            if ((double)V.bnx * V.bny * V.bnz <= (double)kMaxBricks && V.bnx < (1 << 20) && V.bny < (1 << 20) && V.bnz < (1 << 20)) break;
+            h *= 1.2599210498948732;
+        }
+        V.cnx = V.bnx * 4; V.cny = V.bny * 4; V.cnz = V.bnz * 4;
+        V.slack = 1e-3f + 1e-6f * (float)(2.0 * maxabs / h + (double)std::max(V.cnx, std::max(V.cny, V.cnz)));
+        V.n_pts = (uint32_t)n;
+
+        point_key_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_xyz, n, V, k_in, v_in);
+        PCR_LAUNCH_CHECK();
+        int rc = sort_pairs64(ctx, k_in, k_out, v_in, v_out, n, bits_for(nbricks * 64ull));
+        if (rc) return rc;
+        head_flag_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(k_out, n, flags);
+        PCR_LAUNCH_CHECK();
+        rc = exclusive_sum_u32(ctx, flags, ords, n);
+        if (rc) return rc;
+        uint32_t n_cells = 0;
+        rc = read_segment_count(ctx, flags, ords, n, &n_cells);
+        if (rc) return rc;
+        const double ppc = (double)n / (double)n_cells;
+        if (attempt + 1 < max_attempts && (ppc > 12.0 || (ppc < 2.5 && n_cells > 64))) {
+            double ratio = sqrt(6.0 / ppc);                 // points lie on 2-D surfaces: ppc ~ h^2
+            ratio = std::min(std::max(ratio, 0.2), 5.0);
+            h *= ratio;
+            continue;
+        }
+        // ---- accept this cell size: materialise the structure ----
+        PCR_CUDA(g.bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
+        PCR_CUDA(cudaMemsetAsync(g.bricks.p, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
+        PCR_CUDA(g.cell_start.ensure(((size_t)n_cells + 1) * 4));
+        PCR_CUDA(g.pts.ensure((size_t)n * sizeof(float4)));
+        grid_fill_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(k_out, flags, ords, n, n_cells,
+                                                                      g.bricks.as<BrickRec>(), g.cell_start.as<uint32_t>());
+        PCR_LAUNCH_CHECK();
+        gather_points_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(d_xyz, v_out, n, g.pts.as<float4>());
+        PCR_LAUNCH_CHECK();
+        if (sorted_payload_out) {
+            PCR_CUDA(sorted_payload_out->ensure((size_t)n * 4));
+            PCR_CUDA(cudaMemcpyAsync(sorted_payload_out->p, v_out, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        }
+        V.bricks = g.bricks.as<uint4>();
+        V.cell_start = g.cell_start.as<uint32_t>();
+        V.pts = g.pts.as<float4>();
+        g.view = V;
+        g.n_cells = n_cells;
+        g.built = true;
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        return PCR_OK;
+    }
+    return fail(ctx, PCR_ERR_LIMIT, "grid build did not converge");
+}
+
+// ---------------------------------------------------------------------------------------
+// k-NN kernels
+// ---------------------------------------------------------------------------------------
+template <int KCAP>
+__global__ void __launch_bounds__(128) knn_query_kernel(GridView G, const float* __restrict__ q, long long m, int k,
+                                                        float* __restrict__ dist, long long* __restrict__ idx) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    BestK<KCAP> best;
+    best.init(k, 3.0e38f);
+    grid_search(G, qx, qy, qz, best);
+    for (int r = 0; r < k; ++r) {
+        if (r < best.cnt) {
+            dist[i * k + r] = sqrtf(best.d2s[r]);
+            idx[i * k + r] = (long long)__float_as_uint(G.pts[best.poss[r]].w);
+        } else {
+            dist[i * k + r] = __int_as_float(0x7f800000);
+            idx[i * k + r] = (long long)G.n_pts;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) nn_query_kernel(GridView G, const float* __restrict__ q, long long m,
+                                                       float* __restrict__ dist, long long* __restrict__ idx) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float d2;
+    const int pos = grid_nn(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], 3.0e38f, d2);
+    if (pos >= 0) {
+        dist[i] = sqrtf(d2);
+        idx[i] = (long long)__float_as_uint(G.pts[pos].w);
+    } else {
+        dist[i] = __int_as_float(0x7f800000);
+        idx[i] = (long long)G.n_pts;
+    }
+}
+
+// Normal of every target point from its k nearest neighbours (k includes the point itself):
+// float32 sums of p and p p^T in neighbour-rank order, cov = E[pp^T] - mu mu^T in float32
+// (estimate_normals.py:41-72, quirk Q5), eigenvector of the smallest eigenvalue.
+template <int KCAP>
+__global__ void __launch_bounds__(128) normals_kernel(GridView G, int k, float4* __restrict__ nrm_sorted,
+                                                      float* __restrict__ nrm_orig) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= (long long)G.n_pts) return;
+    const float4 self = G.pts[i];
+    BestK<KCAP> best;
+    best.init(k, 3.0e38f);
+    grid_search(G, self.x, self.y, self.z, best);
+    float sx = 0.f, sy = 0.f, sz = 0.f, xx = 0.f, yy = 0.f, zz = 0.f, xy = 0.f, xz = 0.f, yz = 0.f;
+    for (int r = 0; r < best.cnt; ++r) {
+        const float4 t = G.pts[best.poss[r]];
+        sx = fadd_rn(sx, t.x); sy = fadd_rn(sy, t.y); sz = fadd_rn(sz, t.z);
+        xx = fadd_rn(xx, fmul_rn(t.x, t.x)); yy = fadd_rn(yy, fmul_rn(t.y, t.y)); zz = fadd_rn(zz, fmul_rn(t.z, t.z));
+        xy = fadd_rn(xy, fmul_rn(t.x, t.y)); xz = fadd_rn(xz, fmul_rn(t.x, t.z)); yz = fadd_rn(yz, fmul_rn(t.y, t.z));
+    }
+    const float kf = (float)k;
+    const float mx = fdiv_rn(sx, kf), my = fdiv_rn(sy, kf), mz = fdiv_rn(sz, kf);
+    const float cxx = fsub_rn(fdiv_rn(xx, kf), fmul_rn(mx, mx));
+    const float cyy = fsub_rn(fdiv_rn(yy, kf), fmul_rn(my, my));
+    const float czz = fsub_rn(fdiv_rn(zz, kf), fmul_rn(mz, mz));
+    const float cxy = fsub_rn(fdiv_rn(xy, kf), fmul_rn(mx, my));
+    const float cxz = fsub_rn(fdiv_rn(xz, kf), fmul_rn(mx, mz));
+    const float cyz = fsub_rn(fdiv_rn(yz, kf), fmul_rn(my, mz));
+    double vx, vy, vz;
+    smallest_eigvec_sym3(cxx, cxy, cxz, cyy, cyz, czz, vx, vy, vz, nullptr);
+    nrm_sorted[i] = make_float4((float)vx, (float)vy, (float)vz, 0.f);
+    const size_t j = __float_as_uint(self.w);
+    nrm_orig[3 * j] = (float)vx; nrm_orig[3 * j + 1] = (float)vy; nrm_orig[3 * j + 2] = (float)vz;
+}
+
+// caller order (n,3) -> sorted float4 and back
+__global__ void scatter_normals_kernel(const float* __restrict__ nrm_orig, const float4* __restrict__ pts, long long n,
+                                       float4* __restrict__ nrm_sorted) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t j = __float_as_uint(pts[i].w);
+    nrm_sorted[i] = make_float4(nrm_orig[3 * j], nrm_orig[3 * j + 1], nrm_orig[3 * j + 2], 0.f);
+}
+
+// ---------------------------------------------------------------------------------------
+// voxel statistics
+// ---------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T div_rn(T a, T b);
+template <> __device__ __forceinline__ float div_rn<float>(float a, float b) { return __fdiv_rn(a, b); }
+template <> __device__ __forceinline__ double div_rn<double>(double a, double b) { return __ddiv_rn(a, b); }
+
+// voxel coordinate = floor(p / voxel_size) in the INPUT precision (voxel.py:16)
+template <typename T>
+__global__ void voxel_coord_kernel(const T* __restrict__ xyz, long long n, T vs, int* __restrict__ coords, int* __restrict__ mm) {
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            T v = floor(div_rn<T>(xyz[3 * i + a], vs));
+            if (!(v == v)) v = 0;
+            v = v < (T)-1.0e9 ? (T)-1.0e9 : (v > (T)1.0e9 ? (T)1.0e9 : v);
+            const int c = (int)v;
+            coords[3 * i + a] = c;
+            lo[a] = min(lo[a], c); hi[a] = max(hi[a], c);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&mm[a], lo[a]);
+            atomicMax(&mm[3 + a], hi[a]);
+        }
+    }
+}
+
+__global__ void voxel_key_kernel(const int* __restrict__ coords, long long n, int mnx, int mny, int mnz, int bnx, int bny,
+                                 unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int cx = coords[3 * i] - mnx, cy = coords[3 * i + 1] - mny, cz = coords[3 * i + 2] - mnz;
+    unsigned long long brick = ((unsigned long long)(cz >> 2) * bny + (cy >> 2)) * bnx + (cx >> 2);
+    keys[i] = brick * 64ull + (unsigned long long)brick_bit(cx, cy, cz);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void segment_start_kernel(const uint32_t* __restrict__ flags, const uint32_t* __restrict__ ords, long long n,
+                                     uint32_t n_seg, uint32_t* __restrict__ seg) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i == 0) seg[n_seg] = (uint32_t)n;
+    if (i >= n || !flags[i]) return;
+    seg[ords[i]] = (uint32_t)i;
+}
+
+// One thread per occupied voxel: sequential float64 sums in original point order (the radix
+// sort is stable), i.e. the order np.bincount uses (voxel.py:113-143).  Two passes about the
+// mean; sample covariance / max(n-1, 1).
+template <typename T>
+__global__ void voxel_stats_kernel(const T* __restrict__ xyz, const uint32_t* __restrict__ vals, const uint32_t* __restrict__ seg,
+                                   uint32_t n_seg, int min_points, double* __restrict__ mean, double* __restrict__ cov6,
+                                   uint32_t* __restrict__ keep) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_seg) return;
+    const uint32_t s = seg[v], e = seg[v + 1];
+    const double cnt = (double)(e - s);
+    double sx = 0, sy = 0, sz = 0;
+    for (uint32_t p = s; p < e; ++p) {
+        const size_t j = vals[p];
+        sx = dadd_rn(sx, (double)xyz[3 * j]); sy = dadd_rn(sy, (double)xyz[3 * j + 1]); sz = dadd_rn(sz, (double)xyz[3 * j + 2]);
+    }
+    const double mx = ddiv_rn(sx, cnt), my = ddiv_rn(sy, cnt), mz = ddiv_rn(sz, cnt);
+    double cxx = 0, cxy = 0, cxz = 0, cyy = 0, cyz = 0, czz = 0;
+    for (uint32_t p = s; p < e; ++p) {
+        const size_t j = vals[p];
+        const double dx = dsub_rn((double)xyz[3 * j], mx), dy = dsub_rn((double)xyz[3 * j + 1], my), dz = dsub_rn((double)xyz[3 * j + 2], mz);
+        cxx = dadd_rn(cxx, dmul_rn(dx, dx)); cxy = dadd_rn(cxy, dmul_rn(dx, dy)); cxz = dadd_rn(cxz, dmul_rn(dx, dz));
+        cyy = dadd_rn(cyy, dmul_rn(dy, dy)); cyz = dadd_rn(cyz, dmul_rn(dy, dz)); czz = dadd_rn(czz, dmul_rn(dz, dz));
+    }
+    const double den = (e - s) > 1 ? (double)(e - s - 1) : 1.0;
+    mean[3 * (size_t)v] = mx; mean[3 * (size_t)v + 1] = my; mean[3 * (size_t)v + 2] = mz;
+    double* c = cov6 + 6 * (size_t)v;
+    c[0] = ddiv_rn(cxx, den); c[1] = ddiv_rn(cxy, den); c[2] = ddiv_rn(cxz, den);
+    c[3] = ddiv_rn(cyy, den); c[4] = ddiv_rn(cyz, den); c[5] = ddiv_rn(czz, den);
+    keep[v] = ((int)(e - s) >= min_points) ? 1u : 0u;
+}
+
+// Compact kept voxels and derive everything the hot path needs from them.
+__global__ void voxel_finalize_kernel(const unsigned long long* __restrict__ keys_sorted, const uint32_t* __restrict__ seg,
+                                      const uint32_t* __restrict__ keep, const uint32_t* __restrict__ kord, uint32_t n_seg,
+                                      uint32_t n_keep, const double* __restrict__ mean_all, const double* __restrict__ cov6_all,
+                                      int with_icov, double* __restrict__ mean, double* __restrict__ cov, double* __restrict__ norm,
+                                      double* __restrict__ icov, long long* __restrict__ count, BrickRec* __restrict__ bricks,
+                                      uint32_t* __restrict__ cell_start, float4* __restrict__ pts, float4* __restrict__ rec_plane,
+                                      float4* __restrict__ rec_ndt) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v == 0) cell_start[n_keep] = n_keep;
+    if (v >= n_seg || !keep[v]) return;
+    const uint32_t o = kord[v];
+    const double mx = mean_all[3 * (size_t)v], my = mean_all[3 * (size_t)v + 1], mz = mean_all[3 * (size_t)v + 2];
+    const double* c6 = cov6_all + 6 * (size_t)v;
+    mean[3 * (size_t)o] = mx; mean[3 * (size_t)o + 1] = my; mean[3 * (size_t)o + 2] = mz;
+    double C[9] = {c6[0], c6[1], c6[2], c6[1], c6[3], c6[4], c6[2], c6[4], c6[5]};
+    for (int t = 0; t < 9; ++t) cov[9 * (size_t)o + t] = C[t];
+    count[o] = (long long)(seg[v + 1] - seg[v]);
+    double nx, ny, nz;
+    smallest_eigvec_sym3(c6[0], c6[1], c6[2], c6[3], c6[4], c6[5], nx, ny, nz, nullptr);
+    norm[3 * (size_t)o] = nx; norm[3 * (size_t)o + 1] = ny; norm[3 * (size_t)o + 2] = nz;
+    rec_plane[2 * (size_t)o] = make_float4((float)mx, (float)my, (float)mz, 0.f);
+    rec_plane[2 * (size_t)o + 1] = make_float4((float)nx, (float)ny, (float)nz, 0.f);
+    if (with_icov) {
+        double W[9];
+        icov_closed_form(C, W);
+        for (int t = 0; t < 9; ++t) icov[9 * (size_t)o + t] = W[t];
+        rec_ndt[3 * (size_t)o] = make_float4((float)mx, (float)my, (float)mz, (float)W[0]);
+        rec_ndt[3 * (size_t)o + 1] = make_float4((float)W[1], (float)W[2], (float)W[4], (float)W[5]);
+        rec_ndt[3 * (size_t)o + 2] = make_float4((float)W[8], 0.f, 0.f, 0.f);
+    }
+    // NN index over the kept means: one point per cell, cell ordinal == kept ordinal
+    const unsigned long long key = keys_sorted[seg[v]];
+    const unsigned long long brick = key >> 6;
+    atomicOr(&bricks[brick].mask, 1ull << (key & 63ull));
+    atomicMin(&bricks[brick].base, o);
+    cell_start[o] = o;
+    pts[o] = make_float4((float)mx, (float)my, (float)mz, __uint_as_float(o));
+}
+
+__global__ void brick_base_init_kernel(BrickRec* bricks, unsigned long long n) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) { bricks[i].mask = 0ull; bricks[i].base = 0xffffffffu; bricks[i].pad = 0u; }
+}
+
+__global__ void voxel_centroid_kernel(const double* __restrict__ mean_all, uint32_t n_seg, float* __restrict__ out) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_seg) return;
+    out[3 * (size_t)v] = (float)mean_all[3 * (size_t)v];
+    out[3 * (size_t)v + 1] = (float)mean_all[3 * (size_t)v + 1];
+    out[3 * (size_t)v + 2] = (float)mean_all[3 * (size_t)v + 2];
+}
+
+__global__ void voxel_query_kernel(GridView G, const float* __restrict__ q, long long m, const double* __restrict__ mean,
+                                   long long* __restrict__ vidx, double* __restrict__ dist) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float d2;
+    const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+    const int pos = grid_nn(G, qx, qy, qz, 3.0e38f, d2);
+    if (pos >= 0) {
+        const size_t o = __float_as_uint(G.pts[pos].w);
+        const double dx = (double)qx - mean[3 * o], dy = (double)qy - mean[3 * o + 1], dz = (double)qz - mean[3 * o + 2];
+        vidx[i] = (long long)o;
+        dist[i] = sqrt(dx * dx + dy * dy + dz * dz);
+    } else {
+        vidx[i] = (long long)G.n_pts;
+        dist[i] = __longlong_as_double(0x7ff0000000000000ll);
+    }
+}
+
+// Shared front end of pcr_build_voxels / pcr_voxel_filter: upload, voxel coordinates, sort,
+// segments, per-voxel mean / covariance.  Leaves on the device:
+//   tmp_b: sorted keys (u64[n]); tmp_c[n..2n): sorted point indices; seg_buf: u32[n_seg+1];
+//   mean_all / cov6_all / keep (per occupied voxel).
+struct VoxelFront {
+    uint32_t n_seg = 0;
+    int mn[3] = {0, 0, 0};
+    int bn[3] = {0, 0, 0};
+    DevBuf xyz, seg, mean_all, cov6_all, keep;
+    void release() { xyz.release(); seg.release(); mean_all.release(); cov6_all.release(); keep.release(); }
+};
+
+template <typename T>
+static int voxel_front(pcr_ctx* ctx, const void* xyz, long long n, double voxel_size, int min_points, VoxelFront& F) {
+    if (n <= 0) return fail(ctx, PCR_ERR_ARG, "cannot voxelise an empty point set");
+    if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "point count exceeds 2^31-1");
+    if (!(voxel_size > 0)) return fail(ctx, PCR_ERR_ARG, "voxel_size must be positive");
+    const T* d_xyz;
+    if (is_device_pointer(xyz)) {
+        d_xyz = (const T*)xyz;
+    } else {
+        PCR_CUDA(F.xyz.ensure((size_t)n * 3 * sizeof(T)));
+        PCR_CUDA(cudaMemcpyAsync(F.xyz.p, xyz, (size_t)n * 3 * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+        d_xyz = F.xyz.as<T>();
+    }
+    PCR_CUDA(ctx->tmp_e.ensure(64 + (size_t)n * 12));
+    int* d_mm = ctx->tmp_e.as<int>();
+    int* coords = d_mm + 16;
+    init_minmax_kernel<<<1, 32, 0, ctx->stream>>>(d_mm);
+    PCR_LAUNCH_CHECK();
+    voxel_coord_kernel<T><<<min(blocks_for(n, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(d_xyz, n, (T)voxel_size, coords, d_mm);
+    PCR_LAUNCH_CHECK();
+    int h_mm[6];
+    PCR_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    double nb[3];
+    for (int a = 0; a < 3; ++a) {
+        F.mn[a] = h_mm[a];
+        nb[a] = floor(((double)h_mm[3 + a] - (double)h_mm[a]) / 4.0) + 1.0;
+    }
+    if (nb[0] * nb[1] * nb[2] > (double)kMaxBricks || nb[0] > 1e6 || nb[1] > 1e6 || nb[2] > 1e6)
+        return fail(ctx, PCR_ERR_LIMIT, "voxel grid extent too large for the dense brick table; use a larger voxel_size");
+    for (int a = 0; a < 3; ++a) F.bn[a] = (int)nb[a];
+    const unsigned long long nbricks = (unsigned long long)F.bn[0] * F.bn[1] * F.bn[2];
+
+    PCR_CUDA(ctx->tmp_a.ensure((size_t)n * 8));
+    PCR_CUDA(ctx->tmp_b.ensure((size_t)n * 8));
+    PCR_CUDA(ctx->tmp_c.ensure((size_t)n * 4 * 2));
+    PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
+    unsigned long long* k_in = ctx->tmp_a.as<unsigned long long>();
+    unsigned long long* k_out = ctx->tmp_b.as<unsigned long long>();
+    uint32_t* v_in = ctx->tmp_c.as<uint32_t>();
+    uint32_t* v_out = v_in + n;
+    uint32_t* flags = ctx->tmp_d.as<uint32_t>();
+    uint32_t* ords = flags + n;
+    voxel_key_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(coords, n, F.mn[0], F.mn[1], F.mn[2], F.bn[0], F.bn[1], k_in, v_in);
+    PCR_LAUNCH_CHECK();
+    int rc = sort_pairs64(ctx, k_in, k_out, v_in, v_out, n, bits_for(nbricks * 64ull));
+    if (rc) return rc;
+    head_flag_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(k_out, n, flags);
+    PCR_LAUNCH_CHECK();
+    rc = exclusive_sum_u32(ctx, flags, ords, n);
+    if (rc) return rc;
+    rc = read_segment_count(ctx, flags, ords, n, &F.n_seg);
+    if (rc) return rc;
+    PCR_CUDA(F.seg.ensure(((size_t)F.n_seg + 1) * 4));
+    PCR_CUDA(F.mean_all.ensure((size_t)F.n_seg * 3 * 8));
+    PCR_CUDA(F.cov6_all.ensure((size_t)F.n_seg * 6 * 8));
+    PCR_CUDA(F.keep.ensure((size_t)F.n_seg * 4 * 2));
+    segment_start_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(flags, ords, n, F.n_seg, F.seg.as<uint32_t>());
+    PCR_LAUNCH_CHECK();
+    voxel_stats_kernel<T><<<blocks_for(F.n_seg, 128), 128, 0, ctx->stream>>>(d_xyz, v_out, F.seg.as<uint32_t>(), F.n_seg, min_points,
+                                                                            F.mean_all.as<double>(), F.cov6_all.as<double>(),
+                                                                            F.keep.as<uint32_t>());
+    PCR_LAUNCH_CHECK();
+    return PCR_OK;
+}
+
+template <typename T>
+static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double voxel_size, int min_points, int with_icov) {
+    VoxelFront F;
+    int rc = voxel_front<T>(ctx, xyz, n, voxel_size, min_points, F);
+    if (rc) { F.release(); return rc; }
+    uint32_t* keep = F.keep.as<uint32_t>();
+    uint32_t* kord = keep + F.n_seg;
+    rc = exclusive_sum_u32(ctx, keep, kord, F.n_seg);
+    if (rc) { F.release(); return rc; }
+    uint32_t n_keep = 0;
+    rc = read_segment_count(ctx, keep, kord, F.n_seg, &n_keep);
+    if (rc) { F.release(); return rc; }
+
+    ctx->has_voxels = false; ctx->has_icov = false;
+    ctx->vox_grid.release();
+    ctx->n_vox = n_keep; ctx->n_vox_all = F.n_seg; ctx->voxel_size = voxel_size;
+    const size_t nk = n_keep ? n_keep : 1;
+    PCR_CUDA(ctx->vox_mean.ensure(nk * 3 * 8));
+    PCR_CUDA(ctx->vox_cov.ensure(nk * 9 * 8));
+    PCR_CUDA(ctx->vox_norm.ensure(nk * 3 * 8));
+    PCR_CUDA(ctx->vox_icov.ensure(nk * 9 * 8));
+    PCR_CUDA(ctx->vox_count.ensure(nk * 8));
+    PCR_CUDA(ctx->vox_rec_plane.ensure(nk * 2 * sizeof(float4)));
+    PCR_CUDA(ctx->vox_rec_ndt.ensure(nk * 3 * sizeof(float4)));
+    Grid& g = ctx->vox_grid;
+    const unsigned long long nbricks = (unsigned long long)F.bn[0] * F.bn[1] * F.bn[2];
+    PCR_CUDA(g.bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
+    PCR_CUDA(g.cell_start.ensure((nk + 1) * 4));
+    PCR_CUDA(g.pts.ensure(nk * sizeof(float4)));
+    brick_base_init_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(g.bricks.as<BrickRec>(), nbricks);
+    PCR_LAUNCH_CHECK();
+    voxel_finalize_kernel<<<blocks_for(F.n_seg, 128), 128, 0, ctx->stream>>>(
+        ctx->tmp_b.as<unsigned long long>(), F.seg.as<uint32_t>(), keep, kord, F.n_seg, n_keep, F.mean_all.as<double>(),
+        F.cov6_all.as<double>(), with_icov, ctx->vox_mean.as<double>(), ctx->vox_cov.as<double>(), ctx->vox_norm.as<double>(),
+        ctx->vox_icov.as<double>(), ctx->vox_count.as<long long>(), g.bricks.as<BrickRec>(), g.cell_start.as<uint32_t>(),
+        g.pts.as<float4>(), ctx->vox_rec_plane.as<float4>(), ctx->vox_rec_ndt.as<float4>());
+    PCR_LAUNCH_CHECK();
+    GridView V{};
+    V.h = (float)voxel_size;
+    V.inv_h = (float)(1.0 / voxel_size);
+    V.ox = (float)((double)F.mn[0] * voxel_size); V.oy = (float)((double)F.mn[1] * voxel_size); V.oz = (float)((double)F.mn[2] * voxel_size);
+    V.bnx = F.bn[0]; V.bny = F.bn[1]; V.bnz = F.bn[2];
+    V.cnx = V.bnx * 4; V.cny = V.bny * 4; V.cnz = V.bnz * 4;
+    double maxabs = 0;
+    for (int a = 0; a < 3; ++a)
+        maxabs = std::max(maxabs, std::max(fabs((double)F.mn[a]), fabs((double)F.mn[a] + 4.0 * F.bn[a])) * voxel_size);
+    V.slack = 1e-3f + 1e-6f * (float)(2.0 * maxabs / voxel_size + (double)std::max(V.cnx, std::max(V.cny, V.cnz)));
+    V.n_pts = n_keep;
+    V.bricks = g.bricks.as<uint4>();
+    V.cell_start = g.cell_start.as<uint32_t>();
+    V.pts = g.pts.as<float4>();
+    g.view = V;
+    g.n_cells = n_keep;
+    g.built = true;
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    F.release();
+    ctx->has_voxels = true;
+    ctx->has_icov = with_icov != 0;
+    return PCR_OK;
+}
+
+template <typename T>
+static int voxel_filter_impl(pcr_ctx* ctx, const void* xyz, long long n, double voxel_size, float* out, long long* n_out) {
+    VoxelFront F;
+    int rc = voxel_front<T>(ctx, xyz, n, voxel_size, 0, F);
+    if (rc) { F.release(); return rc; }
+    DevBuf d_out;
+    PCR_CUDA(d_out.ensure((size_t)F.n_seg * 12));
+    voxel_centroid_kernel<<<blocks_for(F.n_seg, 256), 256, 0, ctx->stream>>>(F.mean_all.as<double>(), F.n_seg, d_out.as<float>());
+    PCR_LAUNCH_CHECK();
+    const bool dev_out = is_device_pointer(out);
+    PCR_CUDA(cudaMemcpyAsync(out, d_out.p, (size_t)F.n_seg * 12, dev_out ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_out = F.n_seg;
+    d_out.release();
+    F.release();
+    return PCR_OK;
+}
+
+}  // namespace pcr
+
+using namespace pcr;
+
+// =========================================================================================
+// C ABI
+// =========================================================================================
+extern "C" {
+
+int pcr_version(void) { return 100; }
+
+int pcr_device_count(int* count) {
+    pcr_ctx* ctx = nullptr;
+    PCR_CUDA(cudaGetDeviceCount(count));
+    return PCR_OK;
+}
+
+const char* pcr_last_error(const pcr_ctx* ctx) { return ctx ? ctx->err.c_str() : global_error(); }
+
+int pcr_create(int device_id, pcr_ctx** out) {
+    if (!out) return fail(nullptr, PCR_ERR_ARG, "pcr_create: out is NULL");
+    *out = nullptr;
+    pcr_ctx* ctx = nullptr;
+    int ndev = 0;
+    PCR_CUDA(cudaGetDeviceCount(&ndev));
+    if (device_id < 0 || device_id >= ndev)
+        return fail(nullptr, PCR_ERR_ARG, "pcr_create: no CUDA device " + std::to_string(device_id) + " (" + std::to_string(ndev) + " visible)");
+    PCR_CUDA(cudaSetDevice(device_id));
+    cudaDeviceProp prop;
+    PCR_CUDA(cudaGetDeviceProperties(&prop, device_id));
+    if (prop.major < 10)
+        return fail(nullptr, PCR_ERR_CUDA, std::string("pcr_create: device '") + prop.name + "' is not sm_100+; this library ships sm_100a code only");
+    ctx = new pcr_ctx();
+    ctx->device = device_id;
+    ctx->sm_count = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e != cudaSuccess) {
+        std::string m = std::string("pcr_create: ") + cudaGetErrorString(e);
+        delete ctx;
+        return fail(nullptr, PCR_ERR_CUDA, m);
+    }
+    int rc = ensure_loop_buffers(ctx);
+    if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
+    *out = ctx;
+    return PCR_OK;
+}
+
+int pcr_destroy(pcr_ctx* ctx) {
+    if (!ctx) return PCR_OK;
+    cudaSetDevice(ctx->device);
+    pcr_comm_destroy(ctx);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    ctx->tgt_xyz.release(); ctx->tgt_grid.release(); ctx->tgt_nrm_sorted.release(); ctx->tgt_nrm_orig.release();
+    ctx->vox_mean.release(); ctx->vox_cov.release(); ctx->vox_norm.release(); ctx->vox_icov.release(); ctx->vox_count.release();
+    ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
+    ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release();
+    ctx->partials.release(); ctx->state.release();
+    ctx->tmp_a.release(); ctx->tmp_b.release(); ctx->tmp_c.release(); ctx->tmp_d.release(); ctx->tmp_e.release(); ctx->cub_tmp.release();
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return PCR_OK;
+}
+
+int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!xyz || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_set_target_points: empty target");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    ctx->tgt_grid.release();
+    ctx->has_normals = false;
+    PCR_CUDA(ctx->tgt_xyz.ensure((size_t)n * 12));
+    PCR_CUDA(cudaMemcpyAsync(ctx->tgt_xyz.p, xyz, (size_t)n * 12,
+                             is_device_pointer(xyz) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->n_tgt = n;
+    return PCR_OK;
+}
+
+int pcr_build_nn_index(pcr_ctx* ctx) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (ctx->n_tgt <= 0) return fail(ctx, PCR_ERR_STATE, "pcr_build_nn_index: target points not set");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    return build_point_grid(ctx, ctx->tgt_xyz.as<float>(), ctx->n_tgt, ctx->tgt_grid, nullptr);
+}
+
+int pcr_estimate_normals(pcr_ctx* ctx, int k) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "pcr_estimate_normals: NN index not built");
+    if (k < 1 || k > 64) return fail(ctx, PCR_ERR_ARG, "pcr_estimate_normals: k must be in 1..64");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    const long long n = ctx->n_tgt;
+    PCR_CUDA(ctx->tgt_nrm_sorted.ensure((size_t)n * sizeof(float4)));
+    PCR_CUDA(ctx->tgt_nrm_orig.ensure((size_t)n * 12));
+    const int thr = 128, blk = blocks_for(n, thr);
+    float4* ns = ctx->tgt_nrm_sorted.as<float4>();
+    float* no = ctx->tgt_nrm_orig.as<float>();
+    if (k <= 8) normals_kernel<8><<<blk, thr, 0, ctx->stream>>>(ctx->tgt_grid.view, k, ns, no);
+    else if (k <= 16) normals_kernel<16><<<blk, thr, 0, ctx->stream>>>(ctx->tgt_grid.view, k, ns, no);
+    else if (k <= 32) normals_kernel<32><<<blk, thr, 0, ctx->stream>>>(ctx->tgt_grid.view, k, ns, no);
+    else normals_kernel<64><<<blk, thr, 0, ctx->stream>>>(ctx->tgt_grid.view, k, ns, no);
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->has_normals = true;
+    return PCR_OK;
+}
+
+int pcr_set_normals(pcr_ctx* ctx, const float* normals) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "pcr_set_normals: NN index not built");
+    if (!normals) return fail(ctx, PCR_ERR_ARG, "pcr_set_normals: NULL normals");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    const long long n = ctx->n_tgt;
+    PCR_CUDA(ctx->tgt_nrm_sorted.ensure((size_t)n * sizeof(float4)));
+    PCR_CUDA(ctx->tgt_nrm_orig.ensure((size_t)n * 12));
+    PCR_CUDA(cudaMemcpyAsync(ctx->tgt_nrm_orig.p, normals, (size_t)n * 12,
+                             is_device_pointer(normals) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    scatter_normals_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->tgt_nrm_orig.as<float>(), ctx->tgt_grid.view.pts, n,
+                                                                        ctx->tgt_nrm_sorted.as<float4>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->has_normals = true;
+    return PCR_OK;
+}
+
+int pcr_get_normals(pcr_ctx* ctx, float* normals) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->has_normals) return fail(ctx, PCR_ERR_STATE, "pcr_get_normals: no normals");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    PCR_CUDA(cudaMemcpyAsync(normals, ctx->tgt_nrm_orig.p, (size_t)ctx->n_tgt * 12,
+                             is_device_pointer(normals) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PCR_OK;
+}
+
+int pcr_build_voxels(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size, int min_points, int with_icov) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!xyz || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_build_voxels: empty input");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    return is_f64 ? build_voxels_impl<double>(ctx, xyz, n, voxel_size, min_points, with_icov)
+                  : build_voxels_impl<float>(ctx, xyz, n, voxel_size, min_points, with_icov);
+}
+
+int pcr_get_voxel_count(pcr_ctx* ctx, int64_t* n_kept, int64_t* n_occupied) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->has_voxels) return fail(ctx, PCR_ERR_STATE, "pcr_get_voxel_count: voxels not built");
+    if (n_kept) *n_kept = ctx->n_vox;
+    if (n_occupied) *n_occupied = ctx->n_vox_all;
+    return PCR_OK;
+}
+
+int pcr_get_voxels(pcr_ctx* ctx, double* mean, double* cov, double* norm, double* icov, int64_t* count) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->has_voxels) return fail(ctx, PCR_ERR_STATE, "pcr_get_voxels: voxels not built");
+    if (icov && !ctx->has_icov) return fail(ctx, PCR_ERR_STATE, "pcr_get_voxels: inverse covariances were not requested at build time");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    const size_t n = (size_t)ctx->n_vox;
+    if (n) {
+        if (mean) PCR_CUDA(cudaMemcpyAsync(mean, ctx->vox_mean.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        if (cov) PCR_CUDA(cudaMemcpyAsync(cov, ctx->vox_cov.p, n * 72, cudaMemcpyDeviceToHost, ctx->stream));
+        if (norm) PCR_CUDA(cudaMemcpyAsync(norm, ctx->vox_norm.p, n * 24, cudaMemcpyDeviceToHost, ctx->stream));
+        if (icov) PCR_CUDA(cudaMemcpyAsync(icov, ctx->vox_icov.p, n * 72, cudaMemcpyDeviceToHost, ctx->stream));
+        if (count) PCR_CUDA(cudaMemcpyAsync(count, ctx->vox_count.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PCR_OK;
+}
+
+int pcr_knn(pcr_ctx* ctx, const float* queries, int64_t m, int k, float* dist, int64_t* idx) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "pcr_knn: NN index not built");
+    if (k < 1 || k > 64) return fail(ctx, PCR_ERR_ARG, "pcr_knn: k must be in 1..64");
+    if (m <= 0) return PCR_OK;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    DevBuf dq, dd, di;
+    const float* q = queries;
+    if (!is_device_pointer(queries)) {
+        PCR_CUDA(dq.ensure((size_t)m * 12));
+        PCR_CUDA(cudaMemcpyAsync(dq.p, queries, (size_t)m * 12, cudaMemcpyHostToDevice, ctx->stream));
+        q = dq.as<float>();
+    }
+    PCR_CUDA(dd.ensure((size_t)m * k * 4));
+    PCR_CUDA(di.ensure((size_t)m * k * 8));
+    const int thr = 128, blk = blocks_for(m, thr);
+    const GridView& G = ctx->tgt_grid.view;
+    if (k == 1) nn_query_kernel<<<blk, thr, 0, ctx->stream>>>(G, q, m, dd.as<float>(), di.as<long long>());
+    else if (k <= 8) knn_query_kernel<8><<<blk, thr, 0, ctx->stream>>>(G, q, m, k, dd.as<float>(), di.as<long long>());
+    else if (k <= 16) knn_query_kernel<16><<<blk, thr, 0, ctx->stream>>>(G, q, m, k, dd.as<float>(), di.as<long long>());
+    else if (k <= 32) knn_query_kernel<32><<<blk, thr, 0, ctx->stream>>>(G, q, m, k, dd.as<float>(), di.as<long long>());
+    else knn_query_kernel<64><<<blk, thr, 0, ctx->stream>>>(G, q, m, k, dd.as<float>(), di.as<long long>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)m * k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(idx, di.p, (size_t)m * k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    dq.release(); dd.release(); di.release();
+    return PCR_OK;
+}
+
+int pcr_voxel_query(pcr_ctx* ctx, const float* queries, int64_t m, int64_t* vidx, double* dist) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->has_voxels) return fail(ctx, PCR_ERR_STATE, "pcr_voxel_query: voxels not built");
+    if (m <= 0) return PCR_OK;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    DevBuf dq, dd, di;
+    const float* q = queries;
+    if (!is_device_pointer(queries)) {
+        PCR_CUDA(dq.ensure((size_t)m * 12));
+        PCR_CUDA(cudaMemcpyAsync(dq.p, queries, (size_t)m * 12, cudaMemcpyHostToDevice, ctx->stream));
+        q = dq.as<float>();
+    }
+    PCR_CUDA(dd.ensure((size_t)m * 8));
+    PCR_CUDA(di.ensure((size_t)m * 8));
+    voxel_query_kernel<<<blocks_for(m, 128), 128, 0, ctx->stream>>>(ctx->vox_grid.view, q, m, ctx->vox_mean.as<double>(),
+                                                                    di.as<long long>(), dd.as<double>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(vidx, di.p, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    dq.release(); dd.release(); di.release();
+    return PCR_OK;
+}
+
+int pcr_voxel_filter(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size, float* out, int64_t* n_out) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!xyz || !out || !n_out || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_voxel_filter: bad arguments");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    long long no = 0;
+    int rc = is_f64 ? voxel_filter_impl<double>(ctx, xyz, n, voxel_size, out, &no) : voxel_filter_impl<float>(ctx, xyz, n, voxel_size, out, &no);
+    *n_out = no;
+    return rc;
+}
+
+int pcr_index_stats(pcr_ctx* ctx, int which, double* cell_edge, int64_t* n_cells, int64_t* n_bricks, int64_t* n_points) {
+    if (!ctx) return PCR_ERR_ARG;
+    const Grid& g = which == 0 ? ctx->tgt_grid : ctx->vox_grid;
+    if (!g.built) return fail(ctx, PCR_ERR_STATE, "pcr_index_stats: index not built");
+    if (cell_edge) *cell_edge = g.view.h;
+    if (n_cells) *n_cells = g.n_cells;
+    if (n_bricks) *n_bricks = (int64_t)g.view.bnx * g.view.bny * g.view.bnz;
+    if (n_points) *n_points = g.view.n_pts;
+    return PCR_OK;
+}
+
+int pcr_launch_count(pcr_ctx* ctx, int64_t* launches) {
+    if (!ctx || !launches) return PCR_ERR_ARG;
+    *launches = ctx->launches;
+    return PCR_OK;
+}
+
+int pcr_stream(pcr_ctx* ctx, void** stream) {
+    if (!ctx || !stream) return PCR_ERR_ARG;
+    *stream = (void*)ctx->stream;
+    return PCR_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,156 @@
+// Shared definitions for the B200 point-cloud-registration hot path.
+//
+// Everything marked PCR_HD is plain C++ that compiles both as device code (the product) and
+// as host code (ONLY for tests/hostsim, which replays single-query / single-point logic on
+// the CPU so that the index arithmetic can be debugged without a GPU).  The product path
+// never executes the host instantiations.
+#pragma once
+
+#include <cstdint>
+#include <cmath>
+#include <vector_types.h>
+
+#if defined(__CUDACC__)
+#define PCR_HD __host__ __device__ __forceinline__
+#else
+#define PCR_HD inline
+#endif
+
+// ---- method ids (match include/pcr_b200.h) -------------------------------------------
+#define PCR_METHOD_ICP 0
+#define PCR_METHOD_PLANE 1
+#define PCR_METHOD_VPLANE 2
+#define PCR_METHOD_NDT 3
+
+// Normal-equation record produced per linearisation:
+//   [0..20]  upper triangle of H, row major (H00 H01 .. H05 H11 .. H55)
+//   [21..26] g
+//   [27]     e2
+//   [28]     number of inlier correspondences
+#define PCR_NEQ 29
+#define PCR_NEQ_PAD 32
+
+namespace pcr {
+
+PCR_HD int popc64(unsigned long long v) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+
+PCR_HD int ffs64(unsigned long long v) {   // 1-based index of least significant set bit, 0 if none
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)v);
+#else
+    return __builtin_ffsll((long long)v);
+#endif
+}
+
+// IEEE single-rounding float ops that must not be contracted into FMAs (used where the
+// reference's NumPy float32 arithmetic is replayed operation by operation).
+PCR_HD float fmul_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rn(a, b);
+#else
+    volatile float r = a * b; return r;
+#endif
+}
+PCR_HD float fadd_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rn(a, b);
+#else
+    volatile float r = a + b; return r;
+#endif
+}
+PCR_HD float fsub_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rn(a, b);
+#else
+    volatile float r = a - b; return r;
+#endif
+}
+PCR_HD float fdiv_rn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fdiv_rn(a, b);
+#else
+    volatile float r = a / b; return r;
+#endif
+}
+PCR_HD double dmul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+PCR_HD double dadd_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+PCR_HD double dsub_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dsub_rn(a, b);
+#else
+    volatile double r = a - b; return r;
+#endif
+}
+PCR_HD double ddiv_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b; return r;
+#endif
+}
+
+// --------------------------------------------------------------------------------------
+// Two-level sparse uniform grid ("brick grid") used for every exact nearest-neighbour
+// search (target points for ICP/PlaneICP/kNN normals, kept voxel means for VPlaneICP/NDT).
+//
+//   * fine cells of edge h; 4x4x4 cells form a brick
+//   * dense brick table: one 16-byte record per brick = 64-bit occupancy mask of its cells
+//     + ordinal of its first occupied cell in `cell_start`
+//   * cell_start[ordinal] .. cell_start[ordinal+1] = range of the cell's points in `pts`
+//   * pts: float4 (x, y, z, payload index bits), sorted by (brick, cell-in-brick)
+//
+// An empty cell costs no memory traffic beyond its brick record; a query touches
+// 1 brick record + 1-2 cell_start words + the candidate points of the few occupied cells
+// that intersect its current search ball.
+// --------------------------------------------------------------------------------------
+struct GridView {
+    float ox, oy, oz;        // world position of cell (0,0,0)'s low corner
+    float h, inv_h;          // cell edge and its reciprocal
+    float slack;             // conservative inflation (grid units) covering f32 binning error
+    int cnx, cny, cnz;       // cells per axis (multiples of 4)
+    int bnx, bny, bnz;       // bricks per axis
+    const uint4* bricks;     // (mask_lo, mask_hi, first_cell_ordinal, unused)
+    const uint32_t* cell_start;
+    const float4* pts;
+    uint32_t n_pts;
+};
+
+PCR_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+PCR_HD int cell_of(float g, int n) {          // grid coordinate -> clamped cell index
+    int c = (int)floorf(g);
+    return clampi(c, 0, n - 1);
+}
+
+// bit index of cell (x,y,z) inside its brick
+PCR_HD int brick_bit(int cx, int cy, int cz) { return ((cz & 3) << 4) | ((cy & 3) << 2) | (cx & 3); }
+
+// 64-bit mask of the cells of one brick whose local coordinates lie in [x0,x1]x[y0,y1]x[z0,z1]
+// (all in 0..3, inclusive, lo <= hi).
+PCR_HD unsigned long long brick_box_mask(int x0, int x1, int y0, int y1, int z0, int z1) {
+    unsigned long long mx = ((2ull << x1) - (1ull << x0)) * 0x1111111111111111ull;            // x nibble pattern
+    unsigned long long my = ((2ull << (4 * y1 + 3)) - (1ull << (4 * y0))) * 0x0001000100010001ull;  // y rows in every z slab
+    unsigned long long hi = (z1 == 3) ? ~0ull : ((1ull << (16 * (z1 + 1))) - 1ull);
+    unsigned long long mz = hi & ~((1ull << (16 * z0)) - 1ull);
+    return mx & my & mz;
+}
+
+}  // namespace pcr

@@ -1,0 +1,148 @@
+// Host-side context shared by the translation units of libpcr_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/pcr_b200.h"
+#include "pcr_common.cuh"
+
+namespace pcr {
+
+constexpr int kMaxTrace = 256;          // per-iteration e2 trace capacity of the on-device GN loop
+constexpr int kLinThreads = 256;        // threads per block of the linearise kernels
+constexpr int kMaxLinBlocks = 148 * 8;  // upper bound on persistent grid size (partials buffer)
+
+// Device-resident Gauss-Newton loop state (one per context).
+struct LoopState {
+    double T[16];           // current transform, row major
+    double rec[PCR_NEQ_PAD];// last reduced normal-equation record (see pcr_common.cuh)
+    double dx[6];
+    double dx_norm;
+    double e2_trace[kMaxTrace];
+    int iter;               // linearisations executed so far
+    int done;               // 0 running, 1 converged, 2 singular H
+    unsigned int ticket;    // block arrival counter of the running linearise kernel
+    int pad;
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    cudaError_t ensure(size_t want) {
+        if (want <= bytes && p) return cudaSuccess;
+        release();
+        if (want == 0) want = 16;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) bytes = want; else p = nullptr;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr; bytes = 0;
+    }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Grid {
+    GridView view{};
+    DevBuf bricks, cell_start, pts;
+    uint32_t n_cells = 0;     // occupied cells
+    bool built = false;
+    void release() { bricks.release(); cell_start.release(); pts.release(); built = false; n_cells = 0; }
+};
+
+}  // namespace pcr
+
+struct pcr_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int sm_count = 148;
+
+    // ---- target points (ICP / PlaneICP / KDTree facade) ----
+    long long n_tgt = 0;
+    pcr::DevBuf tgt_xyz;          // float[3n], caller order
+    pcr::Grid tgt_grid;           // NN index over target points (payload = caller index)
+    pcr::DevBuf tgt_nrm_sorted;   // float4[n], same order as tgt_grid.pts
+    pcr::DevBuf tgt_nrm_orig;     // float[3n], caller order
+    bool has_normals = false;
+
+    // ---- voxel statistics (VPlaneICP / NDT / VoxelGrid facade) ----
+    long long n_vox = 0;          // kept voxels
+    long long n_vox_all = 0;      // occupied voxels before the min_points filter
+    double voxel_size = 0.0;
+    pcr::DevBuf vox_mean, vox_cov, vox_norm, vox_icov, vox_count;   // double[3n], [9n], [3n], [9n], int64[n]
+    pcr::Grid vox_grid;           // NN index over kept voxel means (payload = voxel ordinal)
+    pcr::DevBuf vox_rec_plane;    // float4[2n]: (mean, 0), (normal, 0)
+    pcr::DevBuf vox_rec_ndt;      // float4[3n]: (mean, W00), (W01, W02, W11, W12), (W22, 0, 0, 0)
+    bool has_voxels = false, has_icov = false;
+
+    // ---- scan ----
+    long long n_scan = 0;         // real points
+    long long n_scan_pad = 0;     // padded to a multiple of 4 with NaN
+    bool scan_set = false;
+    pcr::DevBuf scan_x, scan_y, scan_z;
+    pcr::DevBuf scan_raw;         // staging float[3n]
+
+    // ---- reduction / loop state ----
+    pcr::DevBuf partials;         // double[kMaxLinBlocks * PCR_NEQ_PAD]
+    pcr::DevBuf state;            // LoopState
+    pcr::LoopState* h_state = nullptr;   // pinned host mirror
+    double* h_out = nullptr;             // pinned + mapped: rec[32] + T[16] + {iter, done} written by the kernel
+    double* d_out_mapped = nullptr;      // device alias of h_out
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float last_ms = 0.f;
+    long long launches = 0;       // kernels launched by this context (all kinds)
+
+    // ---- scratch for builds ----
+    pcr::DevBuf tmp_a, tmp_b, tmp_c, tmp_d, tmp_e, cub_tmp;
+
+    // ---- multi-GPU ----
+    void* nccl_lib = nullptr;
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+};
+
+namespace pcr {
+
+void set_global_error(const std::string& s);
+
+inline int fail(pcr_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    set_global_error(msg);
+    return code;
+}
+
+#define PCR_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (call);                                                                    \
+        if (_e != cudaSuccess) {                                                                    \
+            return pcr::fail(ctx, PCR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e) + \
+                                                    " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+        }                                                                                           \
+    } while (0)
+
+#define PCR_LAUNCH_CHECK()                                                                          \
+    do {                                                                                            \
+        cudaError_t _e = cudaGetLastError();                                                        \
+        if (_e != cudaSuccess) {                                                                    \
+            return pcr::fail(ctx, PCR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(_e) + \
+                                                    " (" __FILE__ ":" + std::to_string(__LINE__) + ")"); \
+        }                                                                                           \
+        ctx->launches++;                                                                            \
+    } while (0)
+
+inline bool is_device_pointer(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// internal cross-TU entry points
+int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, DevBuf* sorted_payload_out);
+int ensure_loop_buffers(pcr_ctx* ctx);
+
+}  // namespace pcr

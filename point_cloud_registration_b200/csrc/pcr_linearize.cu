@@ -1,0 +1,644 @@
+// The per-iteration hot path of libpcr_b200.so (sm_100a): ONE fused kernel per Gauss-Newton
+// linearisation
+//
+//   coalesced float4 loads of the SoA scan -> SE(3) transform (float32) -> exact
+//   correspondence search in the brick grid -> residual + 6-DoF Jacobian terms ->
+//   per-thread float32 partial sums -> float64 warp-shuffle + shared-memory block reduction
+//   -> per-block partial record -> the LAST block to arrive sums the partials in a fixed
+//   order (deterministic), assembles the 29-entry record and (on-device loop) performs the
+//   6x6 solve, the stop test and the SE(3) update.
+//
+// Replaces calc_H_g_e2 of icp.py:24-57, plane_icp.py:30-69, voxelized_plane_icp.py:23-64,
+// ndt.py:24-57 and the loop of registration.py:89-111.  No tensor cores: the path is a
+// gather + 29-term reduction (arithmetic intensity ~3 flop/B), bounded by HBM / L2 traffic.
+#include <dlfcn.h>
+
+#include <cub/cub.cuh>
+
+#include "pcr_context.cuh"
+#include "pcr_grid.cuh"
+#include "pcr_linalg.cuh"
+#include "pcr_terms.cuh"
+
+namespace pcr {
+
+struct LinParams {
+    const float* sx; const float* sy; const float* sz;   // SoA scan, padded to a multiple of 4 with NaN
+    long long n_groups;                                  // n_scan_pad / 4
+    GridView grid;                                       // target points (ICP/PLANE) or voxel means (VPLANE/NDT)
+    const float4* nrm;                                   // PLANE: normals in grid order
+    const float4* vrec;                                  // VPLANE: 2 float4 / voxel, NDT: 3 float4 / voxel
+    float max_d2;
+    double T_param[16];
+    int use_param_T;          // 1: transform comes from T_param, 0: from st->T (device loop)
+    int device_loop;          // 1: last block performs the Gauss-Newton step on st
+    int max_iter;
+    double tol;
+    LoopState* st;
+    double* partials;         // [gridDim.x][PCR_NEQ_PAD]
+    double* out_mapped;       // pinned host memory (may be NULL): rec[32], T[16], iter, done
+};
+
+template <int METHOD> struct NAcc { static constexpr int value = PCR_NEQ; };
+template <> struct NAcc<PCR_METHOD_ICP> { static constexpr int value = 17; };
+
+__device__ __forceinline__ float sel4(const float4& v, int u) {
+    return u == 0 ? v.x : (u == 1 ? v.y : (u == 2 ? v.z : v.w));
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kLinThreads) linearize_kernel(const LinParams P) {
+    constexpr int NACC = NAcc<METHOD>::value;
+    constexpr int NWARP = kLinThreads / 32;
+    __shared__ double s_T[16];
+    __shared__ double s_red[NWARP][PCR_NEQ_PAD];
+    __shared__ double s_sum[PCR_NEQ_PAD];
+    __shared__ int s_flag;
+
+    LoopState* st = P.st;
+    if (threadIdx.x == 0) s_flag = P.use_param_T ? 0 : *((volatile int*)&st->done);   // device loop finished?
+    if (threadIdx.x < 16) s_T[threadIdx.x] = P.use_param_T ? P.T_param[threadIdx.x] : ((volatile double*)st->T)[threadIdx.x];
+    __syncthreads();
+    if (s_flag) return;                                   // loop already finished: nothing to do
+
+    Pose32 pose;
+    pose32_from_T(s_T, pose);
+
+    float acc[NACC];
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+
+    const float4* __restrict__ X4 = reinterpret_cast<const float4*>(P.sx);
+    const float4* __restrict__ Y4 = reinterpret_cast<const float4*>(P.sy);
+    const float4* __restrict__ Z4 = reinterpret_cast<const float4*>(P.sz);
+    for (long long grp = blockIdx.x * (long long)kLinThreads + threadIdx.x; grp < P.n_groups;
+         grp += (long long)gridDim.x * kLinThreads) {
+        const float4 xs = __ldg(X4 + grp), ys = __ldg(Y4 + grp), zs = __ldg(Z4 + grp);
+#pragma unroll 1
+        for (int u = 0; u < 4; ++u) {
+            const float px = sel4(xs, u), py = sel4(ys, u), pz = sel4(zs, u);
+            float qx, qy, qz;
+            transform32(pose, px, py, pz, qx, qy, qz);
+            float d2;
+            const int pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+            if (pos < 0) continue;
+            if (METHOD == PCR_METHOD_ICP) {
+                const float4 t = P.grid.pts[pos];
+                accum_icp(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z);
+            } else if (METHOD == PCR_METHOD_PLANE) {
+                const float4 t = P.grid.pts[pos];
+                const float4 nn = __ldg(P.nrm + pos);
+                accum_plane(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z, nn.x, nn.y, nn.z);
+            } else if (METHOD == PCR_METHOD_VPLANE) {
+                const float4 m = __ldg(P.vrec + 2 * (size_t)pos), nn = __ldg(P.vrec + 2 * (size_t)pos + 1);
+                accum_plane(acc, pose, px, py, pz, qx - m.x, qy - m.y, qz - m.z, nn.x, nn.y, nn.z);
+            } else {
+                const float4 a = __ldg(P.vrec + 3 * (size_t)pos), b = __ldg(P.vrec + 3 * (size_t)pos + 1), c = __ldg(P.vrec + 3 * (size_t)pos + 2);
+                const float w6[6] = {a.w, b.x, b.y, b.z, b.w, c.x};
+                accum_ndt(acc, pose, px, py, pz, qx - a.x, qy - a.y, qz - a.z, w6);
+            }
+        }
+    }
+
+    // ---- block reduction: float64 warp shuffles, then across warps through shared memory ----
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) {
+        double v = (double)acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < NWARP; ++w) v += s_red[w][threadIdx.x];
+        P.partials[(size_t)blockIdx.x * PCR_NEQ_PAD + threadIdx.x] = v;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(&st->ticket, 1u);
+        s_flag = (t == gridDim.x - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_flag) return;
+
+    // ---- last block: deterministic final reduction over the per-block partials ----
+    __threadfence();
+    for (int i = warp; i < NACC; i += NWARP) {
+        double v = 0.0;
+        for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(P.partials + (size_t)b * PCR_NEQ_PAD + i);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) s_sum[i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double rec[PCR_NEQ_PAD];
+        if (METHOD == PCR_METHOD_ICP) {
+            assemble_icp(s_sum, s_T, rec);
+        } else {
+#pragma unroll
+            for (int i = 0; i < PCR_NEQ; ++i) rec[i] = s_sum[i];
+        }
+        for (int i = 0; i < PCR_NEQ; ++i) st->rec[i] = rec[i];
+        st->ticket = 0u;
+        int iter = st->iter;
+        int done = 0;
+        if (P.device_loop) {
+            if (iter < kMaxTrace) st->e2_trace[iter] = rec[27];
+            iter += 1;
+            double T[16];
+            for (int i = 0; i < 16; ++i) T[i] = s_T[i];
+            double dx[6], dxn = 0.0;
+            const int rc = gauss_newton_step(rec, P.tol, T, dx, &dxn);
+            if (rc == 0) {
+                for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+                if (iter >= P.max_iter) done = 3;            // iteration budget exhausted
+            } else {
+                done = rc;                                    // 1 converged, 2 singular
+            }
+            for (int i = 0; i < 6; ++i) st->dx[i] = dx[i];
+            st->dx_norm = dxn;
+            st->iter = iter;
+            st->done = done;
+        }
+        if (P.out_mapped) {
+            for (int i = 0; i < PCR_NEQ; ++i) P.out_mapped[i] = rec[i];
+            for (int i = 0; i < 16; ++i) P.out_mapped[32 + i] = P.device_loop ? st->T[i] : s_T[i];
+            P.out_mapped[48] = (double)iter;
+            P.out_mapped[49] = (double)done;
+            __threadfence_system();
+        }
+    }
+}
+
+// Gauss-Newton step as its own tiny kernel (multi-GPU path: runs after the all-reduce).
+__global__ void gn_step_kernel(LoopState* st, double tol, int max_iter) {
+    if (threadIdx.x != 0 || st->done) return;
+    int iter = st->iter;
+    if (iter < kMaxTrace) st->e2_trace[iter] = st->rec[27];
+    iter += 1;
+    double T[16], rec[PCR_NEQ_PAD], dx[6], dxn = 0.0;
+    for (int i = 0; i < 16; ++i) T[i] = st->T[i];
+    for (int i = 0; i < PCR_NEQ; ++i) rec[i] = st->rec[i];
+    int done = 0;
+    const int rc = gauss_newton_step(rec, tol, T, dx, &dxn);
+    if (rc == 0) {
+        for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+        if (iter >= max_iter) done = 3;
+    } else {
+        done = rc;
+    }
+    for (int i = 0; i < 6; ++i) st->dx[i] = dx[i];
+    st->dx_norm = dxn;
+    st->iter = iter;
+    st->done = done;
+}
+
+struct T16 { double v[16]; };
+__global__ void loop_init_kernel(LoopState* st, T16 T0) {
+    if (threadIdx.x < 16) st->T[threadIdx.x] = T0.v[threadIdx.x];
+    if (threadIdx.x == 0) { st->iter = 0; st->done = 0; st->ticket = 0u; st->dx_norm = 0.0; }
+}
+
+// ---------------------------------------------------------------------------------------
+// scan upload: AoS float3 -> (optionally Morton-sorted) SoA, NaN padded to a multiple of 4
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000ffu;
+    v = (v | (v << 8)) & 0x0300f00fu;
+    v = (v | (v << 4)) & 0x030c30c3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+__global__ void morton_key_kernel(const float* __restrict__ xyz, long long n, float ox, float oy, float oz, float scale,
+                                  uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float fx = (xyz[3 * i] - ox) * scale, fy = (xyz[3 * i + 1] - oy) * scale, fz = (xyz[3 * i + 2] - oz) * scale;
+    uint32_t ix = (uint32_t)fminf(fmaxf(fx == fx ? fx : 0.f, 0.f), 1023.f);
+    uint32_t iy = (uint32_t)fminf(fmaxf(fy == fy ? fy : 0.f, 0.f), 1023.f);
+    uint32_t iz = (uint32_t)fminf(fmaxf(fz == fz ? fz : 0.f, 0.f), 1023.f);
+    keys[i] = spread10(ix) | (spread10(iy) << 1) | (spread10(iz) << 2);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void scan_to_soa_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ order, long long n, long long n_pad,
+                                   float* __restrict__ sx, float* __restrict__ sy, float* __restrict__ sz) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    if (i < n) {
+        const size_t j = order ? (size_t)order[i] : (size_t)i;
+        sx[i] = xyz[3 * j]; sy[i] = xyz[3 * j + 1]; sz[i] = xyz[3 * j + 2];
+    } else {
+        const float nan = __int_as_float(0x7fc00000);
+        sx[i] = nan; sy[i] = nan; sz[i] = nan;
+    }
+}
+
+__global__ void scan_bbox_kernel(const float* __restrict__ xyz, long long n, int* __restrict__ mm) {
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = xyz[3 * i + a];
+            if (isfinite(v)) {
+                int o = __float_as_int(v);
+                o = o >= 0 ? o : o ^ 0x7fffffff;
+                lo[a] = min(lo[a], o); hi[a] = max(hi[a], o);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { atomicMin(&mm[a], lo[a]); atomicMax(&mm[3 + a], hi[a]); }
+    }
+}
+
+__global__ void mm_init_kernel(int* mm) {
+    if (threadIdx.x < 3) mm[threadIdx.x] = INT_MAX;
+    else if (threadIdx.x < 6) mm[threadIdx.x] = INT_MIN;
+}
+
+static inline float ord2f(int i) {
+    int j = i >= 0 ? i : i ^ 0x7fffffff;
+    float f;
+    memcpy(&f, &j, 4);
+    return f;
+}
+
+int ensure_loop_buffers(pcr_ctx* ctx) {
+    PCR_CUDA(ctx->partials.ensure((size_t)kMaxLinBlocks * PCR_NEQ_PAD * sizeof(double)));
+    PCR_CUDA(ctx->state.ensure(sizeof(LoopState)));
+    PCR_CUDA(cudaMemsetAsync(ctx->state.p, 0, sizeof(LoopState), ctx->stream));
+    if (!ctx->h_state) PCR_CUDA(cudaHostAlloc((void**)&ctx->h_state, sizeof(LoopState), cudaHostAllocDefault));
+    if (!ctx->h_out) {
+        PCR_CUDA(cudaHostAlloc((void**)&ctx->h_out, 64 * sizeof(double), cudaHostAllocMapped));
+        memset(ctx->h_out, 0, 64 * sizeof(double));
+        PCR_CUDA(cudaHostGetDevicePointer((void**)&ctx->d_out_mapped, ctx->h_out, 0));
+    }
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PCR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// NCCL, resolved at run time so that single-GPU use has no dependency on it
+// ---------------------------------------------------------------------------------------
+typedef struct { char internal[128]; } nccl_uid_t;
+typedef int (*ncclGetUniqueId_t)(nccl_uid_t*);
+typedef int (*ncclCommInitRank_t)(void**, int, nccl_uid_t, int);
+typedef int (*ncclCommDestroy_t)(void*);
+typedef int (*ncclAllReduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef const char* (*ncclGetErrorString_t)(int);
+constexpr int kNcclFloat64 = 8;   // ncclDouble
+constexpr int kNcclSum = 0;       // ncclSum
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclGetUniqueId_t GetUniqueId = nullptr;
+    ncclCommInitRank_t CommInitRank = nullptr;
+    ncclCommDestroy_t CommDestroy = nullptr;
+    ncclAllReduce_t AllReduce = nullptr;
+    ncclGetErrorString_t GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl(pcr_ctx* ctx) {
+    if (g_nccl.lib) return PCR_OK;
+    const char* env = getenv("PCR_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (lib) break;
+    }
+    if (!lib) return fail(ctx, PCR_ERR_NCCL, std::string("cannot dlopen libnccl.so.2 (set PCR_NCCL_LIB): ") + (dlerror() ? dlerror() : ""));
+    g_nccl.GetUniqueId = (ncclGetUniqueId_t)dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (ncclCommInitRank_t)dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (ncclCommDestroy_t)dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllReduce = (ncclAllReduce_t)dlsym(lib, "ncclAllReduce");
+    g_nccl.GetErrorString = (ncclGetErrorString_t)dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllReduce)
+        return fail(ctx, PCR_ERR_NCCL, "libnccl is missing required symbols");
+    g_nccl.lib = lib;
+    return PCR_OK;
+}
+
+static std::string nccl_err(int rc) {
+    return g_nccl.GetErrorString ? std::string(g_nccl.GetErrorString(rc)) : ("nccl error " + std::to_string(rc));
+}
+
+// ---------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------
+static int lin_grid_blocks(pcr_ctx* ctx, long long n_groups, int per_sm) {
+    long long want = (n_groups + kLinThreads - 1) / kLinThreads;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    if (cap > kMaxLinBlocks) cap = kMaxLinBlocks;
+    if (want < 1) want = 1;
+    return (int)(want < cap ? want : cap);
+}
+
+static int check_method(pcr_ctx* ctx, int method) {
+    switch (method) {
+        case PCR_ICP:
+            if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "ICP: target NN index not built");
+            break;
+        case PCR_PLANE:
+            if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "PlaneICP: target NN index not built");
+            if (!ctx->has_normals) return fail(ctx, PCR_ERR_STATE, "PlaneICP: target normals not set");
+            break;
+        case PCR_VPLANE:
+            if (!ctx->has_voxels) return fail(ctx, PCR_ERR_STATE, "VPlaneICP: voxels not built");
+            break;
+        case PCR_NDT:
+            if (!ctx->has_voxels || !ctx->has_icov) return fail(ctx, PCR_ERR_STATE, "NDT: voxels with inverse covariance not built");
+            break;
+        default:
+            return fail(ctx, PCR_ERR_ARG, "unknown method id " + std::to_string(method));
+    }
+    if (!ctx->scan_set) return fail(ctx, PCR_ERR_STATE, "scan not set");
+    return PCR_OK;
+}
+
+static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P) {
+    P.sx = ctx->scan_x.as<float>(); P.sy = ctx->scan_y.as<float>(); P.sz = ctx->scan_z.as<float>();
+    P.n_groups = ctx->n_scan_pad / 4;
+    P.grid = (method == PCR_ICP || method == PCR_PLANE) ? ctx->tgt_grid.view : ctx->vox_grid.view;
+    P.nrm = ctx->tgt_nrm_sorted.as<float4>();
+    P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
+    const float md = (float)max_dist;
+    P.max_d2 = md * md;
+    P.st = ctx->state.as<LoopState>();
+    P.partials = ctx->partials.as<double>();
+    P.out_mapped = ctx->d_out_mapped;
+}
+
+static int launch_linearize(pcr_ctx* ctx, int method, const LinParams& P) {
+    const int blocks = lin_grid_blocks(ctx, P.n_groups, 4);
+    switch (method) {
+        case PCR_ICP: linearize_kernel<PCR_METHOD_ICP><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case PCR_PLANE: linearize_kernel<PCR_METHOD_PLANE><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case PCR_VPLANE: linearize_kernel<PCR_METHOD_VPLANE><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        default: linearize_kernel<PCR_METHOD_NDT><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+    }
+    PCR_LAUNCH_CHECK();
+    return PCR_OK;
+}
+
+static int allreduce_record(pcr_ctx* ctx) {
+    double* rec = ctx->state.as<LoopState>()->rec;
+    int rc = g_nccl.AllReduce(rec, rec, PCR_NEQ, kNcclFloat64, kNcclSum, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return fail(ctx, PCR_ERR_NCCL, "ncclAllReduce: " + nccl_err(rc));
+    return PCR_OK;
+}
+
+}  // namespace pcr
+
+using namespace pcr;
+
+extern "C" {
+
+int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (n < 0 || (n > 0 && !xyz)) return fail(ctx, PCR_ERR_ARG, "pcr_set_scan: bad arguments");
+    if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "pcr_set_scan: point count exceeds 2^31-1");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    ctx->n_scan = n;
+    ctx->n_scan_pad = (n + 3) / 4 * 4;
+    ctx->scan_set = true;
+    if (n == 0) return PCR_OK;
+    const float* d_xyz;
+    if (is_device_pointer(xyz)) {
+        d_xyz = xyz;
+    } else {
+        PCR_CUDA(ctx->scan_raw.ensure((size_t)n * 12));
+        PCR_CUDA(cudaMemcpyAsync(ctx->scan_raw.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        d_xyz = ctx->scan_raw.as<float>();
+    }
+    const size_t pad_bytes = (size_t)ctx->n_scan_pad * 4;
+    PCR_CUDA(ctx->scan_x.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_y.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
+    const uint32_t* order = nullptr;
+    if (sort && n > 1) {
+        PCR_CUDA(ctx->tmp_e.ensure(64));
+        int* d_mm = ctx->tmp_e.as<int>();
+        mm_init_kernel<<<1, 32, 0, ctx->stream>>>(d_mm);
+        PCR_LAUNCH_CHECK();
+        int nb = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
+        scan_bbox_kernel<<<nb, 256, 0, ctx->stream>>>(d_xyz, n, d_mm);
+        PCR_LAUNCH_CHECK();
+        int h_mm[6];
+        PCR_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_mm[0] != INT_MAX) {
+            float lo[3], ext = 0.f;
+            for (int a = 0; a < 3; ++a) { lo[a] = ord2f(h_mm[a]); ext = std::max(ext, ord2f(h_mm[3 + a]) - lo[a]); }
+            const float scale = ext > 0.f ? 1023.999f / ext : 0.f;
+            PCR_CUDA(ctx->tmp_c.ensure((size_t)n * 4 * 2));
+            PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
+            uint32_t* k_in = ctx->tmp_c.as<uint32_t>(); uint32_t* k_out = k_in + n;
+            uint32_t* v_in = ctx->tmp_d.as<uint32_t>(); uint32_t* v_out = v_in + n;
+            morton_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, lo[0], lo[1], lo[2], scale, k_in, v_in);
+            PCR_LAUNCH_CHECK();
+            size_t tmp = 0;
+            PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
+            PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+            PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
+            ctx->launches += 4;
+            order = v_out;
+        }
+    }
+    scan_to_soa_kernel<<<(unsigned)((ctx->n_scan_pad + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, order, n, ctx->n_scan_pad,
+                                                                                         ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
+                                                                                         ctx->scan_z.as<float>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    return PCR_OK;
+}
+
+int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max_dist, int reps) {
+    if (!ctx || !T) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    int rc = check_method(ctx, method);
+    if (rc) return rc;
+    LinParams P{};
+    fill_params(ctx, method, max_dist, P);
+    memcpy(P.T_param, T, sizeof(double) * 16);
+    P.use_param_T = 1; P.device_loop = 0; P.max_iter = 0; P.tol = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        rc = launch_linearize(ctx, method, P);
+        if (rc) return rc;
+        if (ctx->nccl_comm) { rc = allreduce_record(ctx); if (rc) return rc; }
+    }
+    return PCR_OK;
+}
+
+int pcr_linearize(pcr_ctx* ctx, int method, const double T[16], double max_dist, double out[PCR_RECORD_LEN]) {
+    if (!ctx || !T || !out) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    PCR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    int rc = pcr_linearize_async(ctx, method, T, max_dist, 1);
+    if (rc) return rc;
+    PCR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (ctx->nccl_comm) {
+        PCR_CUDA(cudaMemcpyAsync(ctx->h_state->rec, ctx->state.as<LoopState>()->rec, PCR_NEQ * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(out, ctx->h_state->rec, PCR_NEQ * sizeof(double));
+    } else {
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        memcpy(out, ctx->h_out, PCR_NEQ * sizeof(double));
+    }
+    PCR_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return PCR_OK;
+}
+
+int pcr_loop_begin(pcr_ctx* ctx, const double T0[16]) {
+    if (!ctx || !T0) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    T16 t0;
+    memcpy(t0.v, T0, sizeof(t0.v));
+    ctx->h_out[49] = 0.0;
+    loop_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->state.as<LoopState>(), t0);
+    PCR_LAUNCH_CHECK();
+    return PCR_OK;
+}
+
+int pcr_loop_step_async(pcr_ctx* ctx, int method, int max_iter, double tol, double max_dist, int reps) {
+    if (!ctx) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    int rc = check_method(ctx, method);
+    if (rc) return rc;
+    LoopState* st = ctx->state.as<LoopState>();
+    LinParams P{};
+    fill_params(ctx, method, max_dist, P);
+    P.use_param_T = 0; P.max_iter = max_iter; P.tol = tol;
+    const bool multi = ctx->nccl_comm != nullptr;
+    P.device_loop = multi ? 0 : 1;
+    for (int r = 0; r < reps; ++r) {
+        rc = launch_linearize(ctx, method, P);
+        if (rc) return rc;
+        if (multi) {
+            rc = allreduce_record(ctx);
+            if (rc) return rc;
+            gn_step_kernel<<<1, 32, 0, ctx->stream>>>(st, tol, max_iter);
+            PCR_LAUNCH_CHECK();
+        }
+    }
+    return PCR_OK;
+}
+
+int pcr_loop_state(pcr_ctx* ctx, double T_out[16], int* iters, int* done, double* e2_trace, int trace_cap) {
+    if (!ctx) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    PCR_CUDA(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(LoopState), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (T_out) memcpy(T_out, ctx->h_state->T, sizeof(double) * 16);
+    if (iters) *iters = ctx->h_state->iter;
+    if (done) *done = ctx->h_state->done;
+    if (e2_trace && trace_cap > 0)
+        memcpy(e2_trace, ctx->h_state->e2_trace, sizeof(double) * std::min(std::min(ctx->h_state->iter, trace_cap), kMaxTrace));
+    return PCR_OK;
+}
+
+int pcr_align(pcr_ctx* ctx, int method, const double T0[16], int max_iter, double tol, double max_dist, double T_out[16],
+              int* iters, double* e2_trace) {
+    if (!ctx || !T0 || !T_out) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    int rc = check_method(ctx, method);
+    if (rc) return rc;
+    if (max_iter < 0) return fail(ctx, PCR_ERR_ARG, "pcr_align: max_iter < 0");
+    LoopState* st = ctx->state.as<LoopState>();
+    PCR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    rc = pcr_loop_begin(ctx, T0);
+    if (rc) return rc;
+    const bool multi = ctx->nccl_comm != nullptr;
+    int launched = 0;
+    const int chunk = 4;
+    int done = max_iter == 0 ? 3 : 0;
+    while (!done && launched < max_iter) {
+        const int todo = std::min(chunk, max_iter - launched);
+        rc = pcr_loop_step_async(ctx, method, max_iter, tol, max_dist, todo);
+        if (rc) return rc;
+        launched += todo;
+        if (multi) {
+            PCR_CUDA(cudaMemcpyAsync(&ctx->h_state->done, &st->done, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+            done = ctx->h_state->done;
+        } else {
+            PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+            done = (int)ctx->h_out[49];
+        }
+    }
+    PCR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    int n_it = 0, dn = 0;
+    rc = pcr_loop_state(ctx, T_out, &n_it, &dn, e2_trace, max_iter);
+    if (rc) return rc;
+    PCR_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    if (iters) *iters = n_it;
+    if (dn == 2) return fail(ctx, PCR_ERR_SINGULAR, "pcr_align: singular normal equations (no inliers?)");
+    return PCR_OK;
+}
+
+int pcr_last_kernel_ms(pcr_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return PCR_ERR_ARG;
+    *ms = ctx->last_ms;
+    return PCR_OK;
+}
+
+int pcr_comm_unique_id(void* id128) {
+    pcr_ctx* ctx = nullptr;
+    int rc = load_nccl(ctx);
+    if (rc) return rc;
+    nccl_uid_t id;
+    rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail(ctx, PCR_ERR_NCCL, "ncclGetUniqueId: " + nccl_err(rc));
+    memcpy(id128, &id, 128);
+    return PCR_OK;
+}
+
+int pcr_comm_init_rank(pcr_ctx* ctx, int nranks, int rank, const void* id128) {
+    if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, PCR_ERR_ARG, "pcr_comm_init_rank: bad arguments");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    int rc = load_nccl(ctx);
+    if (rc) return rc;
+    pcr_comm_destroy(ctx);
+    nccl_uid_t id;
+    memcpy(&id, id128, 128);
+    void* comm = nullptr;
+    rc = g_nccl.CommInitRank(&comm, nranks, id, rank);
+    if (rc != 0) return fail(ctx, PCR_ERR_NCCL, "ncclCommInitRank: " + nccl_err(rc));
+    ctx->nccl_comm = comm;
+    ctx->nranks = nranks;
+    ctx->rank = rank;
+    return PCR_OK;
+}
+
+int pcr_comm_destroy(pcr_ctx* ctx) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (ctx->nccl_comm && g_nccl.CommDestroy) {
+        cudaStreamSynchronize(ctx->stream);
+        g_nccl.CommDestroy(ctx->nccl_comm);
+    }
+    ctx->nccl_comm = nullptr;
+    ctx->nranks = 1;
+    ctx->rank = 0;
+    return PCR_OK;
+}
+
+}  // extern "C"

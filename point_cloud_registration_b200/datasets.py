@@ -152,3 +152,82 @@ def load_pcd_xyz(path):
         if mode == "ascii":
             return np.loadtxt(fh, dtype=np.float32, usecols=(0, 1, 2)).reshape(-1, 3)
         raise ValueError(f"unsupported PCD DATA mode {mode!r}")
+
+
+def make_urban_slab_torch(n_points, seed=0, density=SURFACE_DENSITY, device="cuda"):
+    """Same scene family as :func:`make_urban_slab`, generated ON THE GPU with torch (used for
+    the 10M / 100M benchmark configurations where host generation would take minutes).  Not
+    bit-identical to the NumPy generator (different random streams).  Returns an (n,3)
+    float32 tensor on ``device``; identical on every GPU for a given (n_points, seed)."""
+    import math
+    import torch
+    g = torch.Generator(device=device)
+    g.manual_seed(int(seed))
+    f64 = dict(dtype=torch.float64, device=device)
+
+    def uni(lo, hi, size):
+        return torch.rand(size, generator=g, **f64) * (hi - lo) + lo
+
+    n = int(n_points)
+    area = n / density
+    n_ground = int(round(0.50 * n))
+    n_wall = int(round(0.35 * n))
+    n_box = n - n_ground - n_wall
+    half = 0.5 * math.sqrt(0.50 * area)
+
+    def ground_z(x, y):
+        return 0.30 * torch.sin(x / 15.0) * torch.cos(y / 11.0)
+
+    out = torch.empty((n, 3), **f64)
+    gx, gy = uni(-half, half, n_ground), uni(-half, half, n_ground)
+    out[:n_ground, 0], out[:n_ground, 1], out[:n_ground, 2] = gx, gy, ground_z(gx, gy)
+    del gx, gy
+
+    wall_area = 0.35 * area
+    n_walls = max(8, int(round(wall_area / 69.0)))
+    w_len, w_hgt = uni(5.0, 20.0, n_walls), uni(3.0, 8.0, n_walls)
+    w_yaw = uni(0.0, math.pi, n_walls)
+    w_cx, w_cy = uni(-half, half, n_walls), uni(-half, half, n_walls)
+    cum = torch.cumsum(w_len * w_hgt, 0)
+    which = torch.searchsorted(cum, uni(0.0, float(cum[-1]), n_wall), right=True).clamp_(max=n_walls - 1)
+    u = uni(-0.5, 0.5, n_wall) * w_len[which]
+    v = uni(0.0, 1.0, n_wall) * w_hgt[which]
+    sl = slice(n_ground, n_ground + n_wall)
+    out[sl, 0] = w_cx[which] + u * torch.cos(w_yaw[which])
+    out[sl, 1] = w_cy[which] + u * torch.sin(w_yaw[which])
+    out[sl, 2] = ground_z(w_cx[which], w_cy[which]) + v
+    del which, u, v
+
+    box_area = max(area - 0.50 * area - wall_area, 1.0)
+    n_boxes = max(4, int(round(box_area / 14.0)))
+    b_sz = uni(1.0, 3.0, (n_boxes, 3))
+    b_cx, b_cy = uni(-half, half, n_boxes), uni(-half, half, n_boxes)
+    which = torch.randint(0, n_boxes, (n_box,), generator=g, device=device)
+    face = torch.randint(0, 5, (n_box,), generator=g, device=device)
+    a, b, c = uni(-0.5, 0.5, n_box), uni(0.0, 1.0, n_box), uni(-0.5, 0.5, n_box)
+    half_p, half_m = torch.full_like(a, 0.5), torch.full_like(a, -0.5)
+    lx = torch.where(face == 0, half_p, torch.where(face == 1, half_m, a)) * b_sz[which, 0]
+    ly = torch.where(face == 2, half_p, torch.where(face == 3, half_m, torch.where(face == 4, c, a))) * b_sz[which, 1]
+    lz = torch.where(face == 4, torch.ones_like(b), b) * b_sz[which, 2]
+    sl = slice(n_ground + n_wall, n)
+    out[sl, 0] = b_cx[which] + lx
+    out[sl, 1] = b_cy[which] + ly
+    out[sl, 2] = ground_z(b_cx[which], b_cy[which]) + lz
+    del which, face, a, b, c, lx, ly, lz
+
+    out += torch.randn(out.shape, generator=g, **f64) * 0.01
+    perm = torch.randperm(n, generator=g, device=device)
+    return out[perm].to(torch.float32).contiguous()
+
+
+def perturb_scan_torch(target, so3=(0.01, -0.02, 0.03), t=(0.1, -0.2, 0.3), sigma=0.005, seed=0):
+    """Device version of :func:`perturb_scan` (full copy, no subsampling)."""
+    import torch
+    g = torch.Generator(device=target.device)
+    g.manual_seed(int(seed) + 7919)
+    R = torch.tensor(rodrigues(so3), dtype=torch.float64, device=target.device)
+    tt = torch.tensor(np.asarray(t, dtype=np.float64), device=target.device)
+    scan = target.to(torch.float64) @ R.T + tt
+    if sigma > 0:
+        scan += torch.randn(scan.shape, generator=g, dtype=torch.float64, device=target.device) * sigma
+    return scan.to(torch.float32).contiguous()

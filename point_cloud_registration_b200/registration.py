@@ -1,0 +1,117 @@
+"""Gauss-Newton driver with the reference's class surface
+(reference point_cloud_registration/registration.py:10-113), backed by libpcr_b200.so.
+
+``align`` keeps the reference signature and semantics (scan cast to float32, stop test BEFORE
+the update, ``ValueError("Target is not set.")``, ``LinAlgError`` on a singular system) but runs
+the whole loop on the GPU (``pcr_align``) unless ``verbose=True`` or ``device_loop=False``, in
+which case the reference's host loop is replayed with one fused-kernel call per iteration."""
+import numpy as np
+
+from . import _lib
+from .math_tools import plus
+
+
+class Registration:
+    method = None      # _lib.ICP / PLANE / VPLANE / NDT, set by subclasses
+
+    def __init__(self, max_iter=30, tol=1e-3):
+        self.max_iter = max_iter
+        self.tol = tol
+        self._is_target_set = False
+        self._ctx = None
+        self._dist = None          # (rank, world_size) once attach_communicator() was called
+        self.sort_scan = True      # Morton-sort the scan on upload in align()
+        self.last_iterations = 0
+        self.last_e2_trace = None
+
+    # -- reference surface --------------------------------------------------------------
+    def is_target_set(self):
+        return self._is_target_set
+
+    def set_target(self, target):
+        raise NotImplementedError("set_target is not implemented.")
+
+    def update_target(self, target):
+        """Declared but not implemented by the reference either (registration.py:36-43)."""
+        raise NotImplementedError("update_target is not implemented.")
+
+    def linearize(self, cur_T, source):
+        """The reference's abstract per-point (J, r, w) hook (registration.py:45-53); the four
+        classes never materialise per-point Jacobians here either."""
+        raise NotImplementedError("linearize is not implemented.")
+
+    def calc_H_g_e2(self, cur_T, source):
+        """One linearisation -> (H (6,6), g (6,), e2).  ``source`` is an (N,3) array (uploaded
+        on every call, like the reference re-reads it) or a handle from :meth:`upload_scan`."""
+        if not self._is_target_set:
+            raise ValueError("Target is not set.")
+        if not isinstance(source, UploadedScan):
+            self._upload(source, sort=False)
+        elif source.owner is not self:
+            raise ValueError("scan handle belongs to another registration object")
+        rec = self._ctx.linearize(self.method, np.asarray(cur_T, dtype=np.float64), self.max_dist)
+        H, g, e2, self.last_inliers = _lib.record_to_H_g_e2(rec)
+        return H, g, e2
+
+    def align(self, source, init_T=np.eye(4), verbose=False, device_loop=None):
+        if self.is_target_set() is False:
+            raise ValueError("Target is not set.")
+        if not isinstance(source, UploadedScan):
+            source = self.upload_scan(source)
+        elif source.owner is not self:
+            raise ValueError("scan handle belongs to another registration object")
+        cur_T = np.asarray(init_T, dtype=np.float64)
+        if device_loop is None:
+            device_loop = not verbose
+        if device_loop:
+            T, iters, trace = self._ctx.align(self.method, cur_T, self.max_iter, self.tol, self.max_dist)
+            self.last_iterations, self.last_e2_trace = iters, trace
+            if verbose:
+                for i, e2 in enumerate(trace):
+                    print(f"iter {i}, error {e2}")
+            return T
+        trace = []
+        for i in range(self.max_iter):
+            H, g, e2 = self.calc_H_g_e2(cur_T, source)
+            trace.append(e2)
+            if verbose:
+                print(f"iter {i}, error {e2}")
+            dx = -np.linalg.solve(H, g)
+            if np.linalg.norm(dx) < self.tol:
+                break
+            cur_T = plus(cur_T, dx)
+        self.last_iterations, self.last_e2_trace = len(trace), np.array(trace)
+        return cur_T
+
+    # -- extensions ---------------------------------------------------------------------
+    def upload_scan(self, source, sort=None):
+        """Upload a scan once and get a handle usable with calc_H_g_e2 / align (avoids the
+        per-call host->device copy the array form implies)."""
+        self._upload(source, sort=self.sort_scan if sort is None else sort)
+        return UploadedScan(self)
+
+    def _upload(self, source, sort):
+        if self._ctx is None:
+            raise ValueError("Target is not set.")
+        src = _lib.as_f32_points(source, "source")               # registration.py:83
+        if self._dist is not None:
+            from .distributed import shard_bounds
+            lo, hi = shard_bounds(src.shape[0], *self._dist)
+            src = src[lo:hi]
+        self._ctx.set_scan(src, sort=sort)
+
+    def attach_communicator(self, rank, world_size, unique_id):
+        """Multi-GPU: this process owns one GPU and one contiguous tile of every scan; the
+        29-double records are all-reduced with NCCL inside the library."""
+        if self._ctx is None:
+            raise ValueError("Target is not set.")
+        self._ctx.comm_init_rank(world_size, rank, unique_id)
+        self._dist = (rank, world_size)
+
+
+class UploadedScan:
+    """Handle to the scan currently resident on the GPU of one registration object."""
+    __slots__ = ("owner",)
+
+    def __init__(self, owner):
+        self.owner = owner

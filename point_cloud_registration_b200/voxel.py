@@ -1,0 +1,78 @@
+"""Voxel grid with the reference's surface (reference point_cloud_registration/voxel.py:12-241):
+``VoxelGrid(voxel_size, min_points=10).set_points(pts)``, ``.calc_icov()``, ``.query(pts, names)``,
+attributes ``mean / cov / norm / icov / kdtree``; ``voxel_filter``; ``get_keys``.  Statistics are
+built on the GPU (csrc/pcr_build.cu).  Voxels are grouped by their EXACT integer coordinate
+``floor(p / voxel_size)`` -- the reference groups by a lossy hash of it (``get_keys``, quirk Q9),
+which is identical whenever that hash has no collision on the data; voxel ORDER is the
+library's own (the reference's, ascending hash key, is an artefact of ``np.unique``)."""
+import numpy as np
+
+from . import _lib
+
+
+def get_keys(points, voxel_size=1.0):
+    """The reference's 64-bit polynomial voxel hash with Python floor-mod semantics
+    (voxel.py:12-21).  Host-side utility kept for API compatibility; the device build does
+    not use it."""
+    c = np.floor(np.asarray(points) / voxel_size).astype(np.int64)
+    p, m = 116101, 10000000000
+    return ((c[:, 2] * p % m + c[:, 1]) * p) % m + c[:, 0]
+
+
+class _MeanIndex:
+    """``VoxelGrid.kdtree``: nearest kept voxel mean (voxel.py:165,176)."""
+
+    def __init__(self, ctx):
+        self._ctx = ctx
+
+    def query(self, pts, k=1):
+        if k != 1:
+            raise NotImplementedError("the voxel-mean index answers k=1 queries only")
+        return self._ctx.voxel_query(_lib.as_f32_points(pts, "query points"))
+
+
+class VoxelGrid:
+    def __init__(self, voxel_size, min_points=10, device=None):
+        self.voxel_size = voxel_size
+        self.min_points = min_points
+        self.kdtree = None
+        self._device = device
+        self._ctx = None
+        self._cache = None
+
+    def set_points(self, points):
+        """voxel.py:104-165 on the GPU (inverse covariances included: they cost nothing extra)."""
+        if self._ctx is None:
+            self._ctx = _lib.Context(self._device)
+        self._ctx.build_voxels(points, self.voxel_size, self.min_points, with_icov=True)
+        self._cache = None
+        self.kdtree = _MeanIndex(self._ctx)
+
+    def calc_icov(self):
+        """Closed-form inverse covariances (voxel.py:69-102); already built by set_points."""
+        if self._ctx is None:
+            raise ValueError("set_points has not been called")
+
+    def _fetch(self):
+        if self._cache is None:
+            mean, cov, norm, icov, count = self._ctx.get_voxels(with_icov=True)
+            self._cache = dict(mean=mean, cov=cov, norm=norm, icov=icov, count=count)
+        return self._cache
+
+    mean = property(lambda self: self._fetch()["mean"])
+    cov = property(lambda self: self._fetch()["cov"])
+    norm = property(lambda self: self._fetch()["norm"])
+    icov = property(lambda self: self._fetch()["icov"])
+    count = property(lambda self: self._fetch()["count"])
+
+    def query(self, points, names):
+        """Nearest kept voxel per point + the requested attributes (voxel.py:171-179)."""
+        dist, idx = self.kdtree.query(points)
+        out = {name: getattr(self, name)[idx] for name in names}
+        out['dist'] = dist
+        return out
+
+
+def voxel_filter(points, voxel_size, device=None):
+    """Per-voxel centroid down-sampling, float32 (voxel.py:209-241), on the GPU."""
+    return _lib.Context(device).voxel_filter(points, voxel_size)

@@ -1,0 +1,147 @@
+// TEST INFRASTRUCTURE ONLY.  Host-side replay of the PCR_HD device functions (grid search,
+// per-point terms, small linear algebra) so that their index arithmetic and algebra can be
+// checked against the oracle on a machine without a GPU.  Built by tests/hostsim/build.py into
+// tests/hostsim/_hostsim.so; never loaded by the product package.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../point_cloud_registration_b200/csrc/pcr_common.cuh"
+#include "../../point_cloud_registration_b200/csrc/pcr_grid.cuh"
+#include "../../point_cloud_registration_b200/csrc/pcr_linalg.cuh"
+#include "../../point_cloud_registration_b200/csrc/pcr_terms.cuh"
+
+using namespace pcr;
+
+struct HostGrid {
+    GridView v{};
+    std::vector<uint4> bricks;
+    std::vector<uint32_t> cell_start;
+    std::vector<float4> pts;
+};
+
+extern "C" {
+
+// Build a brick grid on the host with the same binning arithmetic as point_key_kernel.
+void* hs_grid_build(const float* xyz, int64_t n, double h) {
+    HostGrid* g = new HostGrid();
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    double maxabs = 0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], xyz[3 * i + a]); hi[a] = std::max(hi[a], xyz[3 * i + a]);
+            maxabs = std::max(maxabs, (double)fabsf(xyz[3 * i + a]));
+        }
+    GridView& V = g->v;
+    V.h = (float)h; V.inv_h = (float)(1.0 / h);
+    V.ox = lo[0] - 0.25f * V.h; V.oy = lo[1] - 0.25f * V.h; V.oz = lo[2] - 0.25f * V.h;
+    double c[3];
+    for (int a = 0; a < 3; ++a) c[a] = floor(((double)hi[a] - (double)(lo[a] - 0.25f * V.h)) / h) + 2.0;
+    V.bnx = (int)(c[0] / 4.0 + 1.0); V.bny = (int)(c[1] / 4.0 + 1.0); V.bnz = (int)(c[2] / 4.0 + 1.0);
+    V.cnx = V.bnx * 4; V.cny = V.bny * 4; V.cnz = V.bnz * 4;
+    V.slack = 1e-3f + 1e-6f * (float)(2.0 * maxabs / h + (double)std::max(V.cnx, std::max(V.cny, V.cnz)));
+    V.n_pts = (uint32_t)n;
+    std::vector<unsigned long long> keys(n);
+    for (int64_t i = 0; i < n; ++i) {
+        float gx = (xyz[3 * i] - V.ox) * V.inv_h, gy = (xyz[3 * i + 1] - V.oy) * V.inv_h, gz = (xyz[3 * i + 2] - V.oz) * V.inv_h;
+        int cx = cell_of(gx, V.cnx), cy = cell_of(gy, V.cny), cz = cell_of(gz, V.cnz);
+        unsigned long long brick = ((unsigned long long)(cz >> 2) * V.bny + (cy >> 2)) * V.bnx + (cx >> 2);
+        keys[i] = brick * 64ull + (unsigned long long)brick_bit(cx, cy, cz);
+    }
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    g->bricks.assign((size_t)V.bnx * V.bny * V.bnz, make_uint4(0, 0, 0, 0));
+    g->pts.resize(n);
+    uint32_t ord = 0;
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t j = order[i];
+        float w;
+        memcpy(&w, &j, 4);
+        g->pts[i] = make_float4(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2], w);
+        const unsigned long long key = keys[j];
+        if (i == 0 || key != keys[order[i - 1]]) {
+            g->cell_start.push_back((uint32_t)i);
+            const unsigned long long brick = key >> 6;
+            unsigned long long mask = ((unsigned long long)g->bricks[brick].y << 32) | g->bricks[brick].x;
+            if (mask == 0ull) g->bricks[brick].z = ord;
+            mask |= 1ull << (key & 63ull);
+            g->bricks[brick].x = (uint32_t)mask; g->bricks[brick].y = (uint32_t)(mask >> 32);
+            ++ord;
+        }
+    }
+    g->cell_start.push_back((uint32_t)n);
+    V.bricks = g->bricks.data(); V.cell_start = g->cell_start.data(); V.pts = g->pts.data();
+    return g;
+}
+
+void hs_grid_free(void* g) { delete (HostGrid*)g; }
+int64_t hs_grid_cells(void* g) { return (int64_t)((HostGrid*)g)->cell_start.size() - 1; }
+
+void hs_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, float* dist) {
+    const GridView& G = ((HostGrid*)gp)->v;
+    const float md = (float)max_dist;
+    for (int64_t i = 0; i < m; ++i) {
+        float d2;
+        int pos = grid_nn(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2);
+        if (pos >= 0) {
+            uint32_t j;
+            memcpy(&j, &G.pts[pos].w, 4);
+            idx[i] = j; dist[i] = sqrtf(d2);
+        } else { idx[i] = -1; dist[i] = INFINITY; }
+    }
+}
+
+void hs_knn(void* gp, const float* q, int64_t m, int k, int64_t* idx, float* dist) {
+    const GridView& G = ((HostGrid*)gp)->v;
+    for (int64_t i = 0; i < m; ++i) {
+        BestK<64> best;
+        best.init(k, 3.0e38f);
+        grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], best);
+        for (int r = 0; r < k; ++r) {
+            if (r < best.cnt) {
+                uint32_t j;
+                memcpy(&j, &G.pts[best.poss[r]].w, 4);
+                idx[i * k + r] = j; dist[i * k + r] = sqrtf(best.d2s[r]);
+            } else { idx[i * k + r] = -1; dist[i * k + r] = INFINITY; }
+        }
+    }
+}
+
+// Per-point terms with given correspondences.  rec_in: per scan point the matched record
+//   ICP: q(3) | PLANE/VPLANE: q(3), n(3) | NDT: mu(3), W6(6)   (float32, stride 9), ok flag.
+void hs_linearize(int method, const double* T, const float* scan, int64_t n, const float* recs, const uint8_t* ok,
+                  double* out29) {
+    Pose32 P;
+    pose32_from_T(T, P);
+    double acc[PCR_NEQ_PAD] = {0};
+    for (int64_t i = 0; i < n; ++i) {
+        if (!ok[i]) continue;
+        const float px = scan[3 * i], py = scan[3 * i + 1], pz = scan[3 * i + 2];
+        float qx, qy, qz;
+        transform32(P, px, py, pz, qx, qy, qz);
+        const float* r = recs + 9 * i;
+        if (method == PCR_METHOD_ICP) accum_icp(acc, P, px, py, pz, qx - r[0], qy - r[1], qz - r[2]);
+        else if (method == PCR_METHOD_NDT) accum_ndt(acc, P, px, py, pz, qx - r[0], qy - r[1], qz - r[2], r + 3);
+        else accum_plane(acc, P, px, py, pz, qx - r[0], qy - r[1], qz - r[2], r[3], r[4], r[5]);
+    }
+    if (method == PCR_METHOD_ICP) assemble_icp(acc, T, out29);
+    else for (int i = 0; i < PCR_NEQ; ++i) out29[i] = acc[i];
+}
+
+int hs_gn_step(const double* rec, double tol, double* T, double* dx, double* dxn) { return gauss_newton_step(rec, tol, T, dx, dxn); }
+void hs_so3_exp(const double* w, double* R) { so3_exp(w, R); }
+int hs_solve6(const double* H, const double* g, double* x) { return solve6(H, g, x); }
+void hs_eig3(const double* c6, int64_t n, double* v) {
+    for (int64_t i = 0; i < n; ++i)
+        smallest_eigvec_sym3(c6[6 * i], c6[6 * i + 1], c6[6 * i + 2], c6[6 * i + 3], c6[6 * i + 4], c6[6 * i + 5],
+                             v[3 * i], v[3 * i + 1], v[3 * i + 2], nullptr);
+}
+void hs_icov(const double* cov, int64_t n, double* icov) {
+    for (int64_t i = 0; i < n; ++i) icov_closed_form(cov + 9 * i, icov + 9 * i);
+}
+uint64_t hs_box_mask(int x0, int x1, int y0, int y1, int z0, int z1) { return brick_box_mask(x0, x1, y0, y1, z0, z1); }
+
+}  // extern "C"
