@@ -98,10 +98,12 @@ int pcr_get_voxels(pcr_ctx* ctx, double* mean, double* cov, double* norm, double
 
 /* ---- scan side ------------------------------------------------------------------------- */
 
-/* Upload the scan once per align().  `sort` != 0 re-orders it along a Morton curve on the
- * device (better cache behaviour of the correspondence search; the sums are order
- * independent up to float64 rounding).  Replaces `source.astype(np.float32)`
- * (registration.py:83). */
+/* Upload the scan once per align().  sort > 0 re-orders it along a Morton curve on the device,
+ * which enables the tile-cooperative correspondence search (groups of consecutive scan points
+ * share one candidate list); sort == 0 keeps the caller's order and uses the independent
+ * per-point search; sort < 0 keeps the order but the caller promises it is spatially coherent.
+ * Results are identical up to float64 summation order.  Replaces
+ * `source.astype(np.float32)` (registration.py:83). */
 int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort);
 
 /* ---- per iteration --------------------------------------------------------------------- */
@@ -166,6 +168,14 @@ int pcr_stream(pcr_ctx* ctx, void** stream);
 /* Enqueue `reps` linearisations back to back WITHOUT host synchronisation (benchmark aid:
  * lets the caller bracket them with its own CUDA events on pcr_stream). */
 int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max_dist, int reps);
+/* Lanes per cooperative search tile: 8 (default), 16, 32, or 0 = always the per-point search.
+ * Also settable at context creation through the environment variable PCR_TILE_LANES. */
+int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes);
+/* Test hook: exact NN of every resident scan point (storage order; upload with sort <= 0 to keep
+ * the caller's order) under transform T through the TILE-COOPERATIVE search, against the target
+ * points (which = 0) or the kept voxel means (which = 1); r0 = first search radius in cells.
+ * idx = caller index of the match or -1, dist = Euclidean distance or inf. */
+int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_dist, double r0, int64_t* idx, float* dist);
 /* Grid statistics of the NN indices (cells, bricks, cell edge) for diagnostics. */
 int pcr_index_stats(pcr_ctx* ctx, int which /*0 target, 1 voxel*/, double* cell_edge, int64_t* n_cells,
                     int64_t* n_bricks, int64_t* n_points);

@@ -53,6 +53,8 @@ SYMBOLS = {
     "pcr_launch_count": (_i, [_vp, _pi64]),
     "pcr_stream": (_i, [_vp, C.POINTER(_vp)]),
     "pcr_linearize_async": (_i, [_vp, _i, _vp, _d, _i]),
+    "pcr_set_tile_lanes": (_i, [_vp, _i]),
+    "pcr_debug_tile_nn": (_i, [_vp, _i, _vp, _d, _d, _vp, _vp]),
     "pcr_index_stats": (_i, [_vp, _i, C.POINTER(_d), _pi64, _pi64, _pi64]),
 }
 
@@ -227,7 +229,19 @@ class Context:
 
     # -- scan side ------------------------------------------------------------------------
     def set_scan(self, pts_f32, sort=True):
-        self._check(self._lib.pcr_set_scan(self._h, _ptr(pts_f32), pts_f32.shape[0], int(bool(sort))))
+        """sort: True/1 Morton-sort on the device; False/0 keep order (per-point search);
+        -1 keep order, caller promises spatial coherence (tile-cooperative search)."""
+        self._check(self._lib.pcr_set_scan(self._h, _ptr(pts_f32), pts_f32.shape[0], int(sort)))
+
+    def set_tile_lanes(self, lanes):
+        self._check(self._lib.pcr_set_tile_lanes(self._h, int(lanes)))
+
+    def debug_tile_nn(self, n_scan, T, max_dist, r0=0.5, which=0):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        idx = np.empty(n_scan, dtype=np.int64)
+        dist = np.empty(n_scan, dtype=np.float32)
+        self._check(self._lib.pcr_debug_tile_nn(self._h, int(which), _ptr(T), float(max_dist), float(r0), _ptr(idx), _ptr(dist)))
+        return dist, idx
 
     def linearize(self, method, T, max_dist):
         T = np.ascontiguousarray(T, dtype=np.float64)

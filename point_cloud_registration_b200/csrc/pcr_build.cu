@@ -708,6 +708,10 @@ int pcr_create(int device_id, pcr_ctx** out) {
         delete ctx;
         return fail(nullptr, PCR_ERR_CUDA, m);
     }
+    if (const char* e = getenv("PCR_TILE_LANES")) {
+        const int g = atoi(e);
+        ctx->tile_lanes = (g == 8 || g == 16 || g == 32) ? g : 0;
+    }
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
     *out = ctx;

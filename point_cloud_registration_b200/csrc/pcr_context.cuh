@@ -25,7 +25,7 @@ struct LoopState {
     int iter;               // linearisations executed so far
     int done;               // 0 running, 1 converged, 2 singular H
     unsigned int ticket;    // block arrival counter of the running linearise kernel
-    int pad;
+    float search_r0;        // first search radius (grid cells) suggested for the next linearisation
 };
 
 struct DevBuf {
@@ -82,8 +82,11 @@ struct pcr_ctx {
 
     // ---- scan ----
     long long n_scan = 0;         // real points
-    long long n_scan_pad = 0;     // padded to a multiple of 4 with NaN
+    long long n_scan_pad = 0;     // padded to a multiple of 32 with NaN (whole tiles enter the kernel loop)
     bool scan_set = false;
+    bool scan_sorted = false;     // spatially coherent order -> tile-cooperative search
+    int tile_lanes = 8;           // lanes per cooperative search tile (8/16/32); 0 = per-lane search
+    int lin_blocks_per_sm[4][4] = {};   // cached occupancy per (method, variant)
     pcr::DevBuf scan_x, scan_y, scan_z;
     pcr::DevBuf scan_raw;         // staging float[3n]
 

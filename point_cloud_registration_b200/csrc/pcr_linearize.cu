@@ -19,16 +19,18 @@
 #include "pcr_grid.cuh"
 #include "pcr_linalg.cuh"
 #include "pcr_terms.cuh"
+#include "pcr_tile_search.cuh"
 
 namespace pcr {
 
 struct LinParams {
-    const float* sx; const float* sy; const float* sz;   // SoA scan, padded to a multiple of 4 with NaN
-    long long n_groups;                                  // n_scan_pad / 4
+    const float* sx; const float* sy; const float* sz;   // SoA scan, padded to a multiple of 32 with NaN
+    long long n_pad;                                     // padded point count
     GridView grid;                                       // target points (ICP/PLANE) or voxel means (VPLANE/NDT)
     const float4* nrm;                                   // PLANE: normals in grid order
     const float4* vrec;                                  // VPLANE: 2 float4 / voxel, NDT: 3 float4 / voxel
     float max_d2;
+    float r0_param;           // first search radius (grid units) when use_param_T; <= 0: take st->search_r0
     double T_param[16];
     int use_param_T;          // 1: transform comes from T_param, 0: from st->T (device loop)
     int device_loop;          // 1: last block performs the Gauss-Newton step on st
@@ -39,139 +41,217 @@ struct LinParams {
     double* out_mapped;       // pinned host memory (may be NULL): rec[32], T[16], iter, done
 };
 
+// accumulators per thread: the method's sums + one extra (sum of NN distances, feeds the
+// first-radius heuristic of the next iteration)
 template <int METHOD> struct NAcc { static constexpr int value = PCR_NEQ; };
 template <> struct NAcc<PCR_METHOD_ICP> { static constexpr int value = 17; };
 
-__device__ __forceinline__ float sel4(const float4& v, int u) {
-    return u == 0 ? v.x : (u == 1 ? v.y : (u == 2 ? v.z : v.w));
+struct BlockShared {
+    double T[16];
+    double red[kLinThreads / 32][PCR_NEQ_PAD];
+    double sum[PCR_NEQ_PAD];
+    int flag;
+};
+
+// gather the matched record and add this correspondence's terms
+template <int METHOD>
+__device__ __forceinline__ void accumulate_match(const LinParams& P, const Pose32& pose, float* acc, int pos,
+                                                 float px, float py, float pz, float qx, float qy, float qz) {
+    if (METHOD == PCR_METHOD_ICP) {
+        const float4 t = __ldg(P.grid.pts + pos);
+        accum_icp(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z);
+    } else if (METHOD == PCR_METHOD_PLANE) {
+        const float4 t = __ldg(P.grid.pts + pos);
+        const float4 nn = __ldg(P.nrm + pos);
+        accum_plane(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z, nn.x, nn.y, nn.z);
+    } else if (METHOD == PCR_METHOD_VPLANE) {
+        const float4 m = __ldg(P.vrec + 2 * (size_t)pos), nn = __ldg(P.vrec + 2 * (size_t)pos + 1);
+        accum_plane(acc, pose, px, py, pz, qx - m.x, qy - m.y, qz - m.z, nn.x, nn.y, nn.z);
+    } else {
+        const float4 a = __ldg(P.vrec + 3 * (size_t)pos), b = __ldg(P.vrec + 3 * (size_t)pos + 1), c = __ldg(P.vrec + 3 * (size_t)pos + 2);
+        const float w6[6] = {a.w, b.x, b.y, b.z, b.w, c.x};
+        accum_ndt(acc, pose, px, py, pz, qx - a.x, qy - a.y, qz - a.z, w6);
+    }
 }
 
+// Last block only, one thread: assemble the record, publish it, optionally do the GN step.
 template <int METHOD>
-__global__ void __launch_bounds__(kLinThreads) linearize_kernel(const LinParams P) {
-    constexpr int NACC = NAcc<METHOD>::value;
-    constexpr int NWARP = kLinThreads / 32;
-    __shared__ double s_T[16];
-    __shared__ double s_red[NWARP][PCR_NEQ_PAD];
-    __shared__ double s_sum[PCR_NEQ_PAD];
-    __shared__ int s_flag;
-
+__device__ __noinline__ void finish_iteration(const LinParams& P, BlockShared& sh) {
     LoopState* st = P.st;
-    if (threadIdx.x == 0) s_flag = P.use_param_T ? 0 : *((volatile int*)&st->done);   // device loop finished?
-    if (threadIdx.x < 16) s_T[threadIdx.x] = P.use_param_T ? P.T_param[threadIdx.x] : ((volatile double*)st->T)[threadIdx.x];
-    __syncthreads();
-    if (s_flag) return;                                   // loop already finished: nothing to do
-
-    Pose32 pose;
-    pose32_from_T(s_T, pose);
-
-    float acc[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-
-    const float4* __restrict__ X4 = reinterpret_cast<const float4*>(P.sx);
-    const float4* __restrict__ Y4 = reinterpret_cast<const float4*>(P.sy);
-    const float4* __restrict__ Z4 = reinterpret_cast<const float4*>(P.sz);
-    for (long long grp = blockIdx.x * (long long)kLinThreads + threadIdx.x; grp < P.n_groups;
-         grp += (long long)gridDim.x * kLinThreads) {
-        const float4 xs = __ldg(X4 + grp), ys = __ldg(Y4 + grp), zs = __ldg(Z4 + grp);
-#pragma unroll 1
-        for (int u = 0; u < 4; ++u) {
-            const float px = sel4(xs, u), py = sel4(ys, u), pz = sel4(zs, u);
-            float qx, qy, qz;
-            transform32(pose, px, py, pz, qx, qy, qz);
-            float d2;
-            const int pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
-            if (pos < 0) continue;
-            if (METHOD == PCR_METHOD_ICP) {
-                const float4 t = P.grid.pts[pos];
-                accum_icp(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z);
-            } else if (METHOD == PCR_METHOD_PLANE) {
-                const float4 t = P.grid.pts[pos];
-                const float4 nn = __ldg(P.nrm + pos);
-                accum_plane(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z, nn.x, nn.y, nn.z);
-            } else if (METHOD == PCR_METHOD_VPLANE) {
-                const float4 m = __ldg(P.vrec + 2 * (size_t)pos), nn = __ldg(P.vrec + 2 * (size_t)pos + 1);
-                accum_plane(acc, pose, px, py, pz, qx - m.x, qy - m.y, qz - m.z, nn.x, nn.y, nn.z);
-            } else {
-                const float4 a = __ldg(P.vrec + 3 * (size_t)pos), b = __ldg(P.vrec + 3 * (size_t)pos + 1), c = __ldg(P.vrec + 3 * (size_t)pos + 2);
-                const float w6[6] = {a.w, b.x, b.y, b.z, b.w, c.x};
-                accum_ndt(acc, pose, px, py, pz, qx - a.x, qy - a.y, qz - a.z, w6);
-            }
-        }
+    double rec[PCR_NEQ_PAD];
+    if (METHOD == PCR_METHOD_ICP) {
+        assemble_icp(sh.sum, sh.T, rec);
+    } else {
+        for (int i = 0; i < PCR_NEQ; ++i) rec[i] = sh.sum[i];
     }
+    for (int i = 0; i < PCR_NEQ; ++i) st->rec[i] = rec[i];
+    // first search radius of the next linearisation: 1.25 x mean NN distance, in grid cells
+    const double sum_d = sh.sum[NAcc<METHOD>::value];
+    const double mean_d = rec[28] > 0.0 ? sum_d / rec[28] : 0.0;
+    st->search_r0 = (float)fmin(fmax(1.25 * mean_d * (double)P.grid.inv_h, 0.05), 4.0);
+    st->ticket = 0u;
+    int iter = st->iter;
+    int done = 0;
+    if (P.device_loop) {
+        if (iter < kMaxTrace) st->e2_trace[iter] = rec[27];
+        iter += 1;
+        double T[16];
+        for (int i = 0; i < 16; ++i) T[i] = sh.T[i];
+        double dx[6], dxn = 0.0;
+        const int rc = gauss_newton_step(rec, P.tol, T, dx, &dxn);
+        if (rc == 0) {
+            for (int i = 0; i < 16; ++i) st->T[i] = T[i];
+            if (iter >= P.max_iter) done = 3;            // iteration budget exhausted
+        } else {
+            done = rc;                                    // 1 converged, 2 singular
+        }
+        for (int i = 0; i < 6; ++i) st->dx[i] = dx[i];
+        st->dx_norm = dxn;
+        st->iter = iter;
+        st->done = done;
+    }
+    if (P.out_mapped) {
+        for (int i = 0; i < PCR_NEQ; ++i) P.out_mapped[i] = rec[i];
+        for (int i = 0; i < 16; ++i) P.out_mapped[32 + i] = P.device_loop ? st->T[i] : sh.T[i];
+        P.out_mapped[48] = (double)iter;
+        P.out_mapped[49] = (double)done;
+        __threadfence_system();
+    }
+}
 
-    // ---- block reduction: float64 warp shuffles, then across warps through shared memory ----
+// float32 per-thread sums -> float64 warp shuffles -> shared memory -> per-block partial ->
+// the last block to arrive reduces all partials in a fixed order and finishes the iteration.
+template <int METHOD>
+__device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShared& sh, const float* acc) {
+    constexpr int NRED = NAcc<METHOD>::value + 1;
+    constexpr int NWARP = kLinThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) {
+    for (int i = 0; i < NRED; ++i) {
         double v = (double)acc[i];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) s_red[warp][i] = v;
+        if (lane == 0) sh.red[warp][i] = v;
     }
     __syncthreads();
-    if (threadIdx.x < NACC) {
+    if (threadIdx.x < NRED) {
         double v = 0.0;
 #pragma unroll
-        for (int w = 0; w < NWARP; ++w) v += s_red[w][threadIdx.x];
+        for (int w = 0; w < NWARP; ++w) v += sh.red[w][threadIdx.x];
         P.partials[(size_t)blockIdx.x * PCR_NEQ_PAD + threadIdx.x] = v;
     }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicAdd(&st->ticket, 1u);
-        s_flag = (t == gridDim.x - 1) ? 1 : 0;
+        const unsigned int t = atomicAdd(&P.st->ticket, 1u);
+        sh.flag = (t == gridDim.x - 1) ? 1 : 0;
     }
     __syncthreads();
-    if (!s_flag) return;
-
-    // ---- last block: deterministic final reduction over the per-block partials ----
+    if (!sh.flag) return;
     __threadfence();
-    for (int i = warp; i < NACC; i += NWARP) {
+    for (int i = warp; i < NRED; i += NWARP) {
         double v = 0.0;
         for (unsigned int b = lane; b < gridDim.x; b += 32) v += __ldcg(P.partials + (size_t)b * PCR_NEQ_PAD + i);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) s_sum[i] = v;
+        if (lane == 0) sh.sum[i] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        double rec[PCR_NEQ_PAD];
-        if (METHOD == PCR_METHOD_ICP) {
-            assemble_icp(s_sum, s_T, rec);
-        } else {
+    if (threadIdx.x == 0) finish_iteration<METHOD>(P, sh);
+}
+
+__device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, Pose32& pose, float& r0) {
+    LoopState* st = P.st;
+    if (threadIdx.x == 0) sh.flag = P.use_param_T ? 0 : *((volatile int*)&st->done);   // device loop finished?
+    if (threadIdx.x < 16) sh.T[threadIdx.x] = P.use_param_T ? P.T_param[threadIdx.x] : ((volatile double*)st->T)[threadIdx.x];
+    __syncthreads();
+    if (sh.flag) return false;
+    pose32_from_T(sh.T, pose);
+    r0 = P.r0_param > 0.f ? P.r0_param : *((volatile float*)&st->search_r0);
+    if (!(r0 > 0.f)) r0 = 0.5f;
+    return true;
+}
+
+// ---- variant A: tile-cooperative search (sorted scans) -----------------------------------------
+template <int METHOD, int G>
+__global__ void __launch_bounds__(kLinThreads) linearize_tile_kernel(const LinParams P) {
+    constexpr int NACC = NAcc<METHOD>::value;
+    __shared__ BlockShared sh;
+    __shared__ TileScratch<G> scratch[kLinThreads / G];
+    Pose32 pose;
+    float r0;
+    if (!load_pose(P, sh, pose, r0)) return;                // loop already finished: nothing to do
+
+    float acc[NACC + 1];
 #pragma unroll
-            for (int i = 0; i < PCR_NEQ; ++i) rec[i] = s_sum[i];
+    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
+
+    const cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
+    TileScratch<G>& S = scratch[threadIdx.x / G];
+    const long long stride = (long long)gridDim.x * kLinThreads;
+    for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride) {
+        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);   // coalesced, NaN = padding
+        float qx, qy, qz;
+        transform32(pose, px, py, pz, qx, qy, qz);
+        float d2;
+        int pos;
+        tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
+        if (pos >= 0) {
+            accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
+            acc[NACC] += sqrtf(d2);
         }
-        for (int i = 0; i < PCR_NEQ; ++i) st->rec[i] = rec[i];
-        st->ticket = 0u;
-        int iter = st->iter;
-        int done = 0;
-        if (P.device_loop) {
-            if (iter < kMaxTrace) st->e2_trace[iter] = rec[27];
-            iter += 1;
-            double T[16];
-            for (int i = 0; i < 16; ++i) T[i] = s_T[i];
-            double dx[6], dxn = 0.0;
-            const int rc = gauss_newton_step(rec, P.tol, T, dx, &dxn);
-            if (rc == 0) {
-                for (int i = 0; i < 16; ++i) st->T[i] = T[i];
-                if (iter >= P.max_iter) done = 3;            // iteration budget exhausted
-            } else {
-                done = rc;                                    // 1 converged, 2 singular
-            }
-            for (int i = 0; i < 6; ++i) st->dx[i] = dx[i];
-            st->dx_norm = dxn;
-            st->iter = iter;
-            st->done = done;
+    }
+    reduce_and_finish<METHOD>(P, sh, acc);
+}
+
+// ---- variant B: independent per-lane search (any scan order) -----------------------------------
+template <int METHOD>
+__global__ void __launch_bounds__(kLinThreads) linearize_lane_kernel(const LinParams P) {
+    constexpr int NACC = NAcc<METHOD>::value;
+    __shared__ BlockShared sh;
+    Pose32 pose;
+    float r0;
+    if (!load_pose(P, sh, pose, r0)) return;
+
+    float acc[NACC + 1];
+#pragma unroll
+    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
+    const long long stride = (long long)gridDim.x * kLinThreads;
+    for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride) {
+        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+        float qx, qy, qz;
+        transform32(pose, px, py, pz, qx, qy, qz);
+        float d2;
+        const int pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+        if (pos >= 0) {
+            accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
+            acc[NACC] += sqrtf(d2);
         }
-        if (P.out_mapped) {
-            for (int i = 0; i < PCR_NEQ; ++i) P.out_mapped[i] = rec[i];
-            for (int i = 0; i < 16; ++i) P.out_mapped[32 + i] = P.device_loop ? st->T[i] : s_T[i];
-            P.out_mapped[48] = (double)iter;
-            P.out_mapped[49] = (double)done;
-            __threadfence_system();
-        }
+    }
+    reduce_and_finish<METHOD>(P, sh, acc);
+}
+
+// Debug / test kernel: tile-cooperative NN of the resident scan under T_param -> per scan slot
+// (storage order) the matched position's payload index and the distance.
+template <int G>
+__global__ void __launch_bounds__(kLinThreads) tile_nn_debug_kernel(const LinParams P, long long* __restrict__ idx, float* __restrict__ dist) {
+    __shared__ BlockShared sh;
+    __shared__ TileScratch<G> scratch[kLinThreads / G];
+    Pose32 pose;
+    float r0;
+    if (!load_pose(P, sh, pose, r0)) return;
+    const cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
+    TileScratch<G>& S = scratch[threadIdx.x / G];
+    const long long stride = (long long)gridDim.x * kLinThreads;
+    for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride) {
+        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+        float qx, qy, qz;
+        transform32(pose, px, py, pz, qx, qy, qz);
+        float d2;
+        int pos;
+        tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
+        idx[i] = pos >= 0 ? (long long)__float_as_uint(P.grid.pts[pos].w) : -1ll;
+        dist[i] = pos >= 0 ? sqrtf(d2) : __int_as_float(0x7f800000);
     }
 }
 
@@ -201,7 +281,7 @@ __global__ void gn_step_kernel(LoopState* st, double tol, int max_iter) {
 struct T16 { double v[16]; };
 __global__ void loop_init_kernel(LoopState* st, T16 T0) {
     if (threadIdx.x < 16) st->T[threadIdx.x] = T0.v[threadIdx.x];
-    if (threadIdx.x == 0) { st->iter = 0; st->done = 0; st->ticket = 0u; st->dx_norm = 0.0; }
+    if (threadIdx.x == 0) { st->iter = 0; st->done = 0; st->ticket = 0u; st->dx_norm = 0.0; st->search_r0 = 0.5f; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -345,8 +425,15 @@ static std::string nccl_err(int rc) {
 // ---------------------------------------------------------------------------------------
 // launch helpers
 // ---------------------------------------------------------------------------------------
-static int lin_grid_blocks(pcr_ctx* ctx, long long n_groups, int per_sm) {
-    long long want = (n_groups + kLinThreads - 1) / kLinThreads;
+template <typename K>
+static int blocks_per_sm(K kernel) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kLinThreads, 0) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+    return nb;
+}
+
+static int lin_grid_blocks(pcr_ctx* ctx, long long n_pad, int per_sm) {
+    long long want = (n_pad + kLinThreads - 1) / kLinThreads;
     long long cap = (long long)ctx->sm_count * per_sm;
     if (cap > kMaxLinBlocks) cap = kMaxLinBlocks;
     if (want < 1) want = 1;
@@ -377,7 +464,8 @@ static int check_method(pcr_ctx* ctx, int method) {
 
 static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P) {
     P.sx = ctx->scan_x.as<float>(); P.sy = ctx->scan_y.as<float>(); P.sz = ctx->scan_z.as<float>();
-    P.n_groups = ctx->n_scan_pad / 4;
+    P.n_pad = ctx->n_scan_pad;
+    P.r0_param = 0.f;
     P.grid = (method == PCR_ICP || method == PCR_PLANE) ? ctx->tgt_grid.view : ctx->vox_grid.view;
     P.nrm = ctx->tgt_nrm_sorted.as<float4>();
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
@@ -388,16 +476,38 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.out_mapped = ctx->d_out_mapped;
 }
 
-static int launch_linearize(pcr_ctx* ctx, int method, const LinParams& P) {
-    const int blocks = lin_grid_blocks(ctx, P.n_groups, 4);
-    switch (method) {
-        case PCR_ICP: linearize_kernel<PCR_METHOD_ICP><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case PCR_PLANE: linearize_kernel<PCR_METHOD_PLANE><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case PCR_VPLANE: linearize_kernel<PCR_METHOD_VPLANE><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        default: linearize_kernel<PCR_METHOD_NDT><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+template <int METHOD>
+static int launch_method(pcr_ctx* ctx, const LinParams& P) {
+    // variant: tile-cooperative search for spatially sorted scans, per-lane search otherwise
+    const int G = ctx->scan_sorted ? ctx->tile_lanes : 0;
+    const int v = G == 8 ? 1 : (G == 16 ? 2 : (G == 32 ? 3 : 0));
+    int& per_sm = ctx->lin_blocks_per_sm[METHOD][v];
+    if (per_sm == 0) {
+        switch (v) {
+            case 1: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 8>); break;
+            case 2: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 16>); break;
+            case 3: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 32>); break;
+            default: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD>); break;
+        }
+    }
+    const int blocks = lin_grid_blocks(ctx, P.n_pad, per_sm);
+    switch (v) {
+        case 1: linearize_tile_kernel<METHOD, 8><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 2: linearize_tile_kernel<METHOD, 16><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 3: linearize_tile_kernel<METHOD, 32><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        default: linearize_lane_kernel<METHOD><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
     }
     PCR_LAUNCH_CHECK();
     return PCR_OK;
+}
+
+static int launch_linearize(pcr_ctx* ctx, int method, const LinParams& P) {
+    switch (method) {
+        case PCR_ICP: return launch_method<PCR_METHOD_ICP>(ctx, P);
+        case PCR_PLANE: return launch_method<PCR_METHOD_PLANE>(ctx, P);
+        case PCR_VPLANE: return launch_method<PCR_METHOD_VPLANE>(ctx, P);
+        default: return launch_method<PCR_METHOD_NDT>(ctx, P);
+    }
 }
 
 static int allreduce_record(pcr_ctx* ctx) {
@@ -419,8 +529,10 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
     if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "pcr_set_scan: point count exceeds 2^31-1");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->n_scan = n;
-    ctx->n_scan_pad = (n + 3) / 4 * 4;
+    ctx->n_scan_pad = (n + 31) / 32 * 32;
     ctx->scan_set = true;
+    ctx->scan_sorted = false;
+
     if (n == 0) return PCR_OK;
     const float* d_xyz;
     if (is_device_pointer(xyz)) {
@@ -435,7 +547,7 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
     PCR_CUDA(ctx->scan_y.ensure(pad_bytes));
     PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
     const uint32_t* order = nullptr;
-    if (sort && n > 1) {
+    if (sort > 0 && n > 1) {
         PCR_CUDA(ctx->tmp_e.ensure(64));
         int* d_mm = ctx->tmp_e.as<int>();
         mm_init_kernel<<<1, 32, 0, ctx->stream>>>(d_mm);
@@ -462,8 +574,10 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
             PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
             ctx->launches += 4;
             order = v_out;
+            ctx->scan_sorted = true;
         }
     }
+    if (sort < 0) ctx->scan_sorted = true;      // caller promises a spatially coherent order
     scan_to_soa_kernel<<<(unsigned)((ctx->n_scan_pad + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, order, n, ctx->n_scan_pad,
                                                                                          ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
                                                                                          ctx->scan_z.as<float>());
@@ -592,6 +706,39 @@ int pcr_align(pcr_ctx* ctx, int method, const double T0[16], int max_iter, doubl
     PCR_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
     if (iters) *iters = n_it;
     if (dn == 2) return fail(ctx, PCR_ERR_SINGULAR, "pcr_align: singular normal equations (no inliers?)");
+    return PCR_OK;
+}
+
+int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_dist, double r0, int64_t* idx, float* dist) {
+    if (!ctx || !T || !idx || !dist) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    const Grid& g = which == 0 ? ctx->tgt_grid : ctx->vox_grid;
+    if (!g.built) return fail(ctx, PCR_ERR_STATE, "pcr_debug_tile_nn: index not built");
+    if (!ctx->scan_set || ctx->n_scan == 0) return fail(ctx, PCR_ERR_STATE, "pcr_debug_tile_nn: scan not set");
+    LinParams P{};
+    fill_params(ctx, which == 0 ? PCR_ICP : PCR_VPLANE, max_dist, P);
+    memcpy(P.T_param, T, sizeof(double) * 16);
+    P.use_param_T = 1; P.r0_param = (float)r0;
+    DevBuf di, dd;
+    PCR_CUDA(di.ensure((size_t)ctx->n_scan_pad * 8));
+    PCR_CUDA(dd.ensure((size_t)ctx->n_scan_pad * 4));
+    const int blocks = lin_grid_blocks(ctx, P.n_pad, 2);
+    const int G = ctx->tile_lanes;
+    if (G == 16) tile_nn_debug_kernel<16><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
+    else if (G == 32) tile_nn_debug_kernel<32><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
+    else tile_nn_debug_kernel<8><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaMemcpyAsync(idx, di.p, (size_t)ctx->n_scan * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)ctx->n_scan * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    di.release(); dd.release();
+    return PCR_OK;
+}
+
+int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ctx, PCR_ERR_ARG, "pcr_set_tile_lanes: lanes must be 0, 8, 16 or 32");
+    ctx->tile_lanes = lanes;
     return PCR_OK;
 }
 
