@@ -168,8 +168,9 @@ int pcr_stream(pcr_ctx* ctx, void** stream);
 /* Enqueue `reps` linearisations back to back WITHOUT host synchronisation (benchmark aid:
  * lets the caller bracket them with its own CUDA events on pcr_stream). */
 int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max_dist, int reps);
-/* Lanes per cooperative search tile: 8 (default), 16, 32, or 0 = always the per-point search.
- * Also settable at context creation through the environment variable PCR_TILE_LANES. */
+/* Correspondence-search variant: 0 (default) = independent per-point search, 32 =
+ * warp-cooperative search for sorted scans (kept for A/B measurements; slower on the measured
+ * workloads, see profiles/).  Also settable at context creation through PCR_TILE_LANES. */
 int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes);
 /* Test hook: exact NN of every resident scan point (storage order; upload with sort <= 0 to keep
  * the caller's order) under transform T through the TILE-COOPERATIVE search, against the target

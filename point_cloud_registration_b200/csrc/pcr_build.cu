@@ -190,7 +190,8 @@ int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, Dev
     if (maxext <= 0) maxext = 1.0;
     double vol = 1.0;
     for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * maxext);
-    double h = cbrt(vol * 6.0 / (double)n);
+    const double target_ppc = ctx->target_ppc;
+    double h = cbrt(vol * target_ppc / (double)n);
     h = std::max(h, maxext * 1e-5);
 
     PCR_CUDA(ctx->tmp_a.ensure((size_t)n * 8));
@@ -235,8 +236,8 @@ int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, Dev
         rc = read_segment_count(ctx, flags, ords, n, &n_cells);
         if (rc) return rc;
         const double ppc = (double)n / (double)n_cells;
-        if (attempt + 1 < max_attempts && (ppc > 12.0 || (ppc < 2.5 && n_cells > 64))) {
-            double ratio = sqrt(6.0 / ppc);                 // points lie on 2-D surfaces: ppc ~ h^2
+        if (attempt + 1 < max_attempts && (ppc > 2.0 * target_ppc || (ppc < target_ppc / 2.4 && n_cells > 64))) {
+            double ratio = sqrt(target_ppc / ppc);          // points lie on 2-D surfaces: ppc ~ h^2
             ratio = std::min(std::max(ratio, 0.2), 5.0);
             h *= ratio;
             continue;
@@ -600,6 +601,7 @@ static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     if (rc) { F.release(); return rc; }
 
     ctx->has_voxels = false; ctx->has_icov = false;
+    ctx->vox_grid_epoch++;
     ctx->vox_grid.release();
     ctx->n_vox = n_keep; ctx->n_vox_all = F.n_seg; ctx->voxel_size = voxel_size;
     const size_t nk = n_keep ? n_keep : 1;
@@ -710,8 +712,15 @@ int pcr_create(int device_id, pcr_ctx** out) {
     }
     if (const char* e = getenv("PCR_TILE_LANES")) {
         const int g = atoi(e);
-        ctx->tile_lanes = (g == 8 || g == 16 || g == 32) ? g : 0;
+        ctx->tile_lanes = g == 32 ? 32 : 0;
     }
+    if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) == 3 ? 3 : 2;
+    if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 24.0;
+    if (const char* e = getenv("PCR_R0_MIN")) ctx->r0_min = (float)atof(e);
+    if (const char* e = getenv("PCR_WARM")) ctx->warm_start = atoi(e);
+    if (const char* e = getenv("PCR_SEARCH_MODE")) ctx->search_mode = atoi(e);
+    if (const char* e = getenv("PCR_LOCAL_R1")) ctx->local_r1 = (float)atof(e);
+    if (const char* e = getenv("PCR_LOCAL_R2")) ctx->local_r2 = (float)atof(e);
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
     *out = ctx;
@@ -726,7 +735,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->tgt_xyz.release(); ctx->tgt_grid.release(); ctx->tgt_nrm_sorted.release(); ctx->tgt_nrm_orig.release();
     ctx->vox_mean.release(); ctx->vox_cov.release(); ctx->vox_norm.release(); ctx->vox_icov.release(); ctx->vox_count.release();
     ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
-    ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release();
+    ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();
     ctx->partials.release(); ctx->state.release();
     ctx->tmp_a.release(); ctx->tmp_b.release(); ctx->tmp_c.release(); ctx->tmp_d.release(); ctx->tmp_e.release(); ctx->cub_tmp.release();
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
@@ -756,6 +765,7 @@ int pcr_build_nn_index(pcr_ctx* ctx) {
     if (!ctx) return PCR_ERR_ARG;
     if (ctx->n_tgt <= 0) return fail(ctx, PCR_ERR_STATE, "pcr_build_nn_index: target points not set");
     PCR_CUDA(cudaSetDevice(ctx->device));
+    ctx->tgt_grid_epoch++;
     return build_point_grid(ctx, ctx->tgt_xyz.as<float>(), ctx->n_tgt, ctx->tgt_grid, nullptr);
 }
 

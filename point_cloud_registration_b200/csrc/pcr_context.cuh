@@ -85,9 +85,18 @@ struct pcr_ctx {
     long long n_scan_pad = 0;     // padded to a multiple of 32 with NaN (whole tiles enter the kernel loop)
     bool scan_set = false;
     bool scan_sorted = false;     // spatially coherent order -> tile-cooperative search
-    int tile_lanes = 8;           // lanes per cooperative search tile (8/16/32); 0 = per-lane search
+    int tile_lanes = 0;           // 0: per-point search (default, fastest measured); 32: warp-cooperative search for sorted scans
+    double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
+    float r0_min = 0.0f;          // lower bound of the first cooperative search radius (cells)
+    int warm_start = 0;           // per-point kernel: warm-start the search from the previous matches (measured: no gain)
+    int search_mode = 0;          // see LinParams::search_mode
+    int min_blocks = 2;           // __launch_bounds__ min blocks/SM variant of the tile kernel (2 or 3)
+    float local_r1 = 1.0f, local_r2 = 3.0f;   // warm-start radii (cells) handled by the per-lane searches
     int lin_blocks_per_sm[4][4] = {};   // cached occupancy per (method, variant)
     pcr::DevBuf scan_x, scan_y, scan_z;
+    pcr::DevBuf scan_prev;        // int[n_pad]: position matched by the previous linearisation (warm start)
+    int prev_which = -1;          // index the positions refer to (0 target grid, 1 voxel grid, -1 none)
+    long long prev_epoch = -1, tgt_grid_epoch = 0, vox_grid_epoch = 0;
     pcr::DevBuf scan_raw;         // staging float[3n]
 
     // ---- reduction / loop state ----

@@ -104,6 +104,54 @@ PCR_HD void visit_block(const GridView& G, float qx, float qy, float qz, float g
     }
 }
 
+// Same contract as visit_block for SMALL boxes (a few cells per axis): one flattened loop over
+// the cells, the brick record cached while consecutive cells share a brick.  Much lighter than
+// the brick-mask walk when the ball of the current best meets only a handful of cells -- the
+// common case once a candidate is known (late Gauss-Newton iterations, voxel-mean grids).
+template <class Best>
+PCR_HD void visit_small_box(const GridView& G, float qx, float qy, float qz, float gx, float gy, float gz,
+                            const Block3& nb, const Block3& ob, bool have_old, Best& best) {
+    const int nx = nb.x1 - nb.x0 + 1, ny = nb.y1 - nb.y0 + 1;
+    const int n = nx * ny * (nb.z1 - nb.z0 + 1);
+    const float h2 = G.h * G.h;
+    long long cur_brick = -1;
+    unsigned long long occ = 0ull;
+    uint32_t base = 0u;
+    int cx = nb.x0, cy = nb.y0, cz = nb.z0;
+    for (int k = 0; k < n; ++k) {
+        const bool seen = have_old && cx >= ob.x0 && cx <= ob.x1 && cy >= ob.y0 && cy <= ob.y1 && cz >= ob.z0 && cz <= ob.z1;
+        if (!seen) {
+            const long long b = ((long long)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2);
+            if (b != cur_brick) {
+                const uint4 rec = G.bricks[b];
+                occ = ((unsigned long long)rec.y << 32) | rec.x;
+                base = rec.z;
+                cur_brick = b;
+            }
+            const int bit = brick_bit(cx, cy, cz);
+            if ((occ >> bit) & 1ull) {
+                const float dx = fmaxf(fmaxf((float)cx - gx, gx - (float)(cx + 1)) - G.slack, 0.0f);
+                const float dy = fmaxf(fmaxf((float)cy - gy, gy - (float)(cy + 1)) - G.slack, 0.0f);
+                const float dz = fmaxf(fmaxf((float)cz - gz, gz - (float)(cz + 1)) - G.slack, 0.0f);
+                if ((dx * dx + dy * dy + dz * dz) * h2 < best.radius2()) {
+                    const uint32_t ord = base + (uint32_t)popc64(occ & ((1ull << bit) - 1ull));
+                    const uint32_t s = G.cell_start[ord], e = G.cell_start[ord + 1];
+                    for (uint32_t p = s; p < e; ++p) {
+                        const float4 t = G.pts[p];
+                        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+                        best.offer(ex * ex + ey * ey + ez * ez, (int)p);
+                    }
+                }
+            }
+        }
+        if (++cx > nb.x1) { cx = nb.x0; if (++cy > nb.y1) { cy = nb.y0; ++cz; } }
+    }
+}
+
+PCR_HD bool is_small_box(const Block3& b) {
+    return (b.x1 - b.x0) <= 2 && (b.y1 - b.y0) <= 2 && (b.z1 - b.z0) <= 2;
+}
+
 // Generic exact search.  `best` carries the initial radius (max_dist^2) and receives results.
 template <class Best>
 PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& best) {
@@ -122,10 +170,21 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
     const float big = 1.0e9f;
     const float cgx = fminf(fmaxf(gx, -big), big), cgy = fminf(fmaxf(gy, -big), big), cgz = fminf(fmaxf(gz, -big), big);
     Block3 cur;
+    Block3 none; none.x0 = none.y0 = none.z0 = 0; none.x1 = none.y1 = none.z1 = -1;
+    if (best.have()) {
+        // warm start: the caller already holds a candidate (an upper bound).  Every closer point
+        // lies in a cell meeting the ball (query, bound): visit exactly that box and stop.
+        const float r = sqrtf(best.radius2()) * G.inv_h * 1.000001f + G.slack;
+        cur.x0 = cell_of(fminf(fmaxf(gx - r, -big), big), G.cnx); cur.x1 = cell_of(fminf(fmaxf(gx + r, -big), big), G.cnx);
+        cur.y0 = cell_of(fminf(fmaxf(gy - r, -big), big), G.cny); cur.y1 = cell_of(fminf(fmaxf(gy + r, -big), big), G.cny);
+        cur.z0 = cell_of(fminf(fmaxf(gz - r, -big), big), G.cnz); cur.z1 = cell_of(fminf(fmaxf(gz + r, -big), big), G.cnz);
+        if (is_small_box(cur)) visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+        else visit_block(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+        return;
+    }
     cur.x0 = cur.x1 = cell_of(cgx, G.cnx);
     cur.y0 = cur.y1 = cell_of(cgy, G.cny);
     cur.z0 = cur.z1 = cell_of(cgz, G.cnz);
-    Block3 none; none.x0 = none.y0 = none.z0 = 0; none.x1 = none.y1 = none.z1 = -1;
     visit_block(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
     for (;;) {
         // distance (grid units) from the query to the nearest face of the visited block that
@@ -152,7 +211,8 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
             nb.x0 = nb.x0 < cur.x0 ? nb.x0 : cur.x0; nb.x1 = nb.x1 > cur.x1 ? nb.x1 : cur.x1;
             nb.y0 = nb.y0 < cur.y0 ? nb.y0 : cur.y0; nb.y1 = nb.y1 > cur.y1 ? nb.y1 : cur.y1;
             nb.z0 = nb.z0 < cur.z0 ? nb.z0 : cur.z0; nb.z1 = nb.z1 > cur.z1 ? nb.z1 : cur.z1;
-            visit_block(G, qx, qy, qz, gx, gy, gz, nb, cur, true, best);
+            if (is_small_box(nb)) visit_small_box(G, qx, qy, qz, gx, gy, gz, nb, cur, true, best);
+            else visit_block(G, qx, qy, qz, gx, gy, gz, nb, cur, true, best);
             return;                                          // ball fully covered
         }
         nb.x0 = cur.x0 > 0 ? cur.x0 - 1 : 0; nb.x1 = cur.x1 < G.cnx - 1 ? cur.x1 + 1 : cur.x1;
@@ -166,6 +226,21 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
 // 1-NN convenience wrapper: returns position in G.pts (or -1) and the squared distance.
 PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2, float& out_d2) {
     Best1 b; b.d2 = max_d2; b.pos = -1;
+    grid_search(G, qx, qy, qz, b);
+    out_d2 = b.d2;
+    return b.pos;
+}
+
+// 1-NN with a warm start: `warm_pos` is the position of any indexed point (e.g. the previous
+// iteration's match, -1 = none); its distance bounds the search.
+PCR_HD int grid_nn_warm(const GridView& G, float qx, float qy, float qz, float max_d2, int warm_pos, float& out_d2) {
+    Best1 b; b.d2 = max_d2; b.pos = -1;
+    if (warm_pos >= 0) {
+        const float4 t = G.pts[warm_pos];
+        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+        const float dw = ex * ex + ey * ey + ez * ez;
+        if (dw < max_d2) { b.d2 = dw; b.pos = warm_pos; }
+    }
     grid_search(G, qx, qy, qz, b);
     out_d2 = b.d2;
     return b.pos;

@@ -21,6 +21,10 @@
 #include "pcr_terms.cuh"
 #include "pcr_tile_search.cuh"
 
+#ifndef PCR_LANE_MINB
+#define PCR_LANE_MINB 2
+#endif
+
 namespace pcr {
 
 struct LinParams {
@@ -29,7 +33,12 @@ struct LinParams {
     GridView grid;                                       // target points (ICP/PLANE) or voxel means (VPLANE/NDT)
     const float4* nrm;                                   // PLANE: normals in grid order
     const float4* vrec;                                  // VPLANE: 2 float4 / voxel, NDT: 3 float4 / voxel
+    int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
+    float local_r1, local_r2; // mode 1: warm-start radius (cells) up to which the per-lane local search is used
+    float r0_min;             // lower bound of the first cooperative search radius (cells)
+    int warm;                 // per-point kernel: use P.prev as warm start
+    int search_mode;          // 0: bound + packed pruned search (default); 1: local / cooperative (A/B)
     float r0_param;           // first search radius (grid units) when use_param_T; <= 0: take st->search_r0
     double T_param[16];
     int use_param_T;          // 1: transform comes from T_param, 0: from st->T (device loop)
@@ -169,12 +178,13 @@ __device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, P
     pose32_from_T(sh.T, pose);
     r0 = P.r0_param > 0.f ? P.r0_param : *((volatile float*)&st->search_r0);
     if (!(r0 > 0.f)) r0 = 0.5f;
+    if (P.r0_min > r0) r0 = P.r0_min;
     return true;
 }
 
 // ---- variant A: tile-cooperative search (sorted scans) -----------------------------------------
-template <int METHOD, int G>
-__global__ void __launch_bounds__(kLinThreads) linearize_tile_kernel(const LinParams P) {
+template <int METHOD, int G, int MINB>
+__global__ void __launch_bounds__(kLinThreads, MINB) linearize_tile_kernel(const LinParams P) {
     constexpr int NACC = NAcc<METHOD>::value;
     __shared__ BlockShared sh;
     __shared__ TileScratch<G> scratch[kLinThreads / G];
@@ -193,9 +203,34 @@ __global__ void __launch_bounds__(kLinThreads) linearize_tile_kernel(const LinPa
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);   // coalesced, NaN = padding
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
-        float d2;
-        int pos;
-        tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
+        // warm start: last iteration's match bounds this iteration's search radius
+        float d2 = P.max_d2;
+        int pos = __ldg(P.prev + i);
+        if (pos >= 0) {
+            const float4 t = __ldg(P.grid.pts + pos);
+            const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+            const float dw = ex * ex + ey * ey + ez * ez;
+            if (dw < P.max_d2) d2 = dw; else pos = -1;
+        }
+        const bool valid = px == px;
+        if (P.search_mode == 0) {
+            // mode 0: bound (warm start or cooperative first-hit search), then the packed pruned search
+            if (tile.any(valid && pos < 0)) tile_nn_search<G>(tile, P.grid, S, valid && pos < 0, qx, qy, qz, r0, P.max_d2, d2, pos, true);
+            warp_pruned_search<G>(tile, P.grid, valid && pos >= 0, qx, qy, qz, d2, pos);
+        } else {
+            // mode 1 (kept for A/B): per-lane local search for tight bounds, cooperative search otherwise
+            bool need = valid;
+            if (pos >= 0) {
+                const float r = sqrtf(d2) * P.grid.inv_h * 1.000001f + P.grid.slack;
+                if (r <= P.local_r1) {
+                    const float gx = (qx - P.grid.ox) * P.grid.inv_h, gy = (qy - P.grid.oy) * P.grid.inv_h, gz = (qz - P.grid.oz) * P.grid.inv_h;
+                    local_nn_search(P.grid, qx, qy, qz, gx, gy, gz, r, d2, pos);
+                    need = false;
+                }
+            }
+            if (tile.any(need)) tile_nn_search<G>(tile, P.grid, S, need, qx, qy, qz, r0, P.max_d2, d2, pos);
+        }
+        P.prev[i] = pos;
         if (pos >= 0) {
             accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
             acc[NACC] += sqrtf(d2);
@@ -206,7 +241,7 @@ __global__ void __launch_bounds__(kLinThreads) linearize_tile_kernel(const LinPa
 
 // ---- variant B: independent per-lane search (any scan order) -----------------------------------
 template <int METHOD>
-__global__ void __launch_bounds__(kLinThreads) linearize_lane_kernel(const LinParams P) {
+__global__ void __launch_bounds__(kLinThreads, PCR_LANE_MINB) linearize_lane_kernel(const LinParams P) {
     constexpr int NACC = NAcc<METHOD>::value;
     __shared__ BlockShared sh;
     Pose32 pose;
@@ -222,7 +257,8 @@ __global__ void __launch_bounds__(kLinThreads) linearize_lane_kernel(const LinPa
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
         float d2;
-        const int pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+        const int pos = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? __ldg(P.prev + i) : -1, d2);
+        P.prev[i] = pos;
         if (pos >= 0) {
             accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
             acc[NACC] += sqrtf(d2);
@@ -247,9 +283,14 @@ __global__ void __launch_bounds__(kLinThreads) tile_nn_debug_kernel(const LinPar
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
-        float d2;
-        int pos;
-        tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
+        float d2 = P.max_d2;
+        int pos = -1;
+        if (P.search_mode == 0) {
+            tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos, true);
+            warp_pruned_search<G>(tile, P.grid, pos >= 0, qx, qy, qz, d2, pos);
+        } else {
+            tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
+        }
         idx[i] = pos >= 0 ? (long long)__float_as_uint(P.grid.pts[pos].w) : -1ll;
         dist[i] = pos >= 0 ? sqrtf(d2) : __int_as_float(0x7f800000);
     }
@@ -468,6 +509,12 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.r0_param = 0.f;
     P.grid = (method == PCR_ICP || method == PCR_PLANE) ? ctx->tgt_grid.view : ctx->vox_grid.view;
     P.nrm = ctx->tgt_nrm_sorted.as<float4>();
+    P.prev = ctx->scan_prev.as<int>();
+    P.local_r1 = ctx->local_r1;
+    P.local_r2 = ctx->local_r2;
+    P.search_mode = ctx->search_mode;
+    P.warm = ctx->warm_start;
+    P.r0_min = ctx->r0_min;
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
     const float md = (float)max_dist;
     P.max_d2 = md * md;
@@ -479,29 +526,30 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
 template <int METHOD>
 static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     // variant: tile-cooperative search for spatially sorted scans, per-lane search otherwise
-    const int G = ctx->scan_sorted ? ctx->tile_lanes : 0;
-    const int v = G == 8 ? 1 : (G == 16 ? 2 : (G == 32 ? 3 : 0));
+    // (sub-warp tiles were measured and rejected: the tiles of one warp diverge from each other,
+    //  so their costs add up instead of overlapping -- profiles/r1_notes.md)
+    const int v = (ctx->scan_sorted && ctx->tile_lanes == 32) ? (ctx->min_blocks == 3 ? 2 : 1) : 0;
     int& per_sm = ctx->lin_blocks_per_sm[METHOD][v];
-    if (per_sm == 0) {
-        switch (v) {
-            case 1: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 8>); break;
-            case 2: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 16>); break;
-            case 3: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 32>); break;
-            default: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD>); break;
-        }
-    }
+    if (per_sm == 0)
+        per_sm = v == 2 ? blocks_per_sm(linearize_tile_kernel<METHOD, 32, 3>)
+                        : (v == 1 ? blocks_per_sm(linearize_tile_kernel<METHOD, 32, 2>) : blocks_per_sm(linearize_lane_kernel<METHOD>));
     const int blocks = lin_grid_blocks(ctx, P.n_pad, per_sm);
-    switch (v) {
-        case 1: linearize_tile_kernel<METHOD, 8><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 2: linearize_tile_kernel<METHOD, 16><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 3: linearize_tile_kernel<METHOD, 32><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        default: linearize_lane_kernel<METHOD><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-    }
+    if (v == 2) linearize_tile_kernel<METHOD, 32, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
+    else if (v == 1) linearize_tile_kernel<METHOD, 32, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
+    else linearize_lane_kernel<METHOD><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
     PCR_LAUNCH_CHECK();
     return PCR_OK;
 }
 
 static int launch_linearize(pcr_ctx* ctx, int method, const LinParams& P) {
+    // warm-start positions refer to one particular index: forget them when it changed
+    const int which = (method == PCR_ICP || method == PCR_PLANE) ? 0 : 1;
+    const long long epoch = which == 0 ? ctx->tgt_grid_epoch : ctx->vox_grid_epoch;
+    if (ctx->prev_which != which || ctx->prev_epoch != epoch) {
+        PCR_CUDA(cudaMemsetAsync(ctx->scan_prev.p, 0xFF, (size_t)ctx->n_scan_pad * 4, ctx->stream));
+        ctx->prev_which = which;
+        ctx->prev_epoch = epoch;
+    }
     switch (method) {
         case PCR_ICP: return launch_method<PCR_METHOD_ICP>(ctx, P);
         case PCR_PLANE: return launch_method<PCR_METHOD_PLANE>(ctx, P);
@@ -546,6 +594,8 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
     PCR_CUDA(ctx->scan_x.ensure(pad_bytes));
     PCR_CUDA(ctx->scan_y.ensure(pad_bytes));
     PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_prev.ensure(pad_bytes));
+    ctx->prev_which = -1;                       // new scan: no warm start
     const uint32_t* order = nullptr;
     if (sort > 0 && n > 1) {
         PCR_CUDA(ctx->tmp_e.ensure(64));
@@ -723,10 +773,7 @@ int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_di
     PCR_CUDA(di.ensure((size_t)ctx->n_scan_pad * 8));
     PCR_CUDA(dd.ensure((size_t)ctx->n_scan_pad * 4));
     const int blocks = lin_grid_blocks(ctx, P.n_pad, 2);
-    const int G = ctx->tile_lanes;
-    if (G == 16) tile_nn_debug_kernel<16><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
-    else if (G == 32) tile_nn_debug_kernel<32><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
-    else tile_nn_debug_kernel<8><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
+    tile_nn_debug_kernel<32><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
     PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaMemcpyAsync(idx, di.p, (size_t)ctx->n_scan * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)ctx->n_scan * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -737,7 +784,7 @@ int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_di
 
 int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes) {
     if (!ctx) return PCR_ERR_ARG;
-    if (lanes != 0 && lanes != 8 && lanes != 16 && lanes != 32) return fail(ctx, PCR_ERR_ARG, "pcr_set_tile_lanes: lanes must be 0, 8, 16 or 32");
+    if (lanes != 0 && lanes != 32) return fail(ctx, PCR_ERR_ARG, "pcr_set_tile_lanes: lanes must be 0 (per-point search) or 32 (warp-cooperative search)");
     ctx->tile_lanes = lanes;
     return PCR_OK;
 }

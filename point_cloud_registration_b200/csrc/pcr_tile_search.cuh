@@ -36,6 +36,8 @@ template <int G>
 struct TileScratch {
     float4 cand[G * kTileQuota];   // staged candidates, .w = position in GridView::pts (int bits)
     uint2 cells[4 * G];            // (start, length) of occupied cells still to be staged
+    float4 pad[2];                 // sizeof % 128 == 32: the tiles of one warp broadcast-read
+                                   // cand[k] from different banks (no 4-way conflict for G = 8)
 };
 
 __device__ __forceinline__ int cell_clamped(float g, int n) {
@@ -44,15 +46,64 @@ __device__ __forceinline__ int cell_clamped(float g, int n) {
     return c < 0 ? 0 : (c > n - 1 ? n - 1 : c);
 }
 
+// Fast path for a query that already has a tight upper bound (warm start from the previous
+// Gauss-Newton iteration): visit the few cells that meet the ball (query, sqrt(best_d2)) --
+// at most 3 per axis when the radius is <= one cell -- pruned by their box distance.  Purely
+// per lane; all lanes run the same flattened loop over their (<= 27) cells.
+__device__ __forceinline__ void local_nn_search(const GridView& Gv, float qx, float qy, float qz, float gx, float gy, float gz,
+                                                float r, float& best_d2, int& best_pos) {
+    const int lx = cell_clamped(gx - r, Gv.cnx), hx = cell_clamped(gx + r, Gv.cnx);
+    const int ly = cell_clamped(gy - r, Gv.cny), hy = cell_clamped(gy + r, Gv.cny);
+    const int lz = cell_clamped(gz - r, Gv.cnz), hz = cell_clamped(gz + r, Gv.cnz);
+    const int nx = hx - lx + 1, ny = hy - ly + 1;
+    const int n = nx * ny * (hz - lz + 1);
+    const float h2 = Gv.h * Gv.h;
+    int cur_brick = -1;
+    unsigned long long occ = 0ull;
+    uint32_t base = 0u;
+    int cx = lx, cy = ly, cz = lz;
+    for (int k = 0; k < n; ++k) {
+        const int b = ((cz >> 2) * Gv.bny + (cy >> 2)) * Gv.bnx + (cx >> 2);
+        if (b != cur_brick) {
+            const uint4 rec = __ldg(Gv.bricks + b);
+            occ = ((unsigned long long)rec.y << 32) | rec.x;
+            base = rec.z;
+            cur_brick = b;
+        }
+        const int bit = brick_bit(cx, cy, cz);
+        if ((occ >> bit) & 1ull) {
+            const float dx = fmaxf(fmaxf((float)cx - gx, gx - (float)(cx + 1)) - Gv.slack, 0.0f);
+            const float dy = fmaxf(fmaxf((float)cy - gy, gy - (float)(cy + 1)) - Gv.slack, 0.0f);
+            const float dz = fmaxf(fmaxf((float)cz - gz, gz - (float)(cz + 1)) - Gv.slack, 0.0f);
+            if ((dx * dx + dy * dy + dz * dz) * h2 < best_d2) {
+                const uint32_t ord = base + (uint32_t)__popcll(occ & ((1ull << bit) - 1ull));
+                const uint32_t s = __ldg(Gv.cell_start + ord), e = __ldg(Gv.cell_start + ord + 1);
+                for (uint32_t p = s; p < e; ++p) {
+                    const float4 t = __ldg(Gv.pts + p);
+                    const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+                    const float d2 = ex * ex + ey * ey + ez * ez;
+                    if (d2 < best_d2) { best_d2 = d2; best_pos = (int)p; }
+                }
+            }
+        }
+        if (++cx > hx) { cx = lx; if (++cy > hy) { cy = ly; ++cz; } }
+    }
+}
+
 // Searches for the nearest point of every lane's query.  All lanes of the tile must call it
-// (lanes without a query pass valid = false).  r0 = first search radius in grid units.
+// (lanes without a query pass valid = false).  On entry (best_d2, best_pos) is either
+// (max_dist^2, -1) or a WARM START: the squared distance to / position of any indexed point
+// (e.g. the previous iteration's match) -- an upper bound that lets the lane search the box
+// of that ball at once.  r0 = first search radius in grid units for lanes without a warm start.
+//
+// first_hit = true turns the search into a BOUND FINDER: a lane leaves as soon as it holds any
+// candidate (or is proven to have none within max_dist); warp_pruned_search then makes the
+// result exact.
 template <int G>
 __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& tile, const GridView& Gv, TileScratch<G>& S,
                                                bool valid, float qx, float qy, float qz, float r0, float max_d2,
-                                               float& best_d2, int& best_pos) {
+                                               float& best_d2, int& best_pos, bool first_hit = false) {
     constexpr int LISTCAP = 4 * G;
-    best_d2 = max_d2;
-    best_pos = -1;
     const float gx = (qx - Gv.ox) * Gv.inv_h, gy = (qy - Gv.oy) * Gv.inv_h, gz = (qz - Gv.oz) * Gv.inv_h;
     bool pending = valid && (gx == gx) && (gy == gy) && (gz == gz) && Gv.n_pts != 0;
     if (pending) {   // farther from the whole grid than max_dist: no match possible
@@ -62,10 +113,13 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
         const float e = fmaxf(sqrtf(ex * ex + ey * ey + ez * ez) - Gv.slack, 0.0f) * Gv.h;
         if (e * e >= max_d2) pending = false;
     }
+    if (best_pos >= 0) r0 = sqrtf(best_d2) * Gv.inv_h * 1.000001f + Gv.slack;     // warm start: box of the ball
     int lo0 = cell_clamped(gx - r0, Gv.cnx), hi0 = cell_clamped(gx + r0, Gv.cnx);
     int lo1 = cell_clamped(gy - r0, Gv.cny), hi1 = cell_clamped(gy + r0, Gv.cny);
     int lo2 = cell_clamped(gz - r0, Gv.cnz), hi2 = cell_clamped(gz + r0, Gv.cnz);
     const int rank = tile.thread_rank();
+    // box visited by the previous round (every lane of the tile evaluated all of its points)
+    int p0 = 0, p1 = 0, p2 = 0, w0 = -1, w1 = -1, w2 = -1;
 
     for (;;) {
         const unsigned act = tile.ballot(pending);
@@ -83,6 +137,8 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
         const int v0 = cg::reduce(tile, member ? hi0 : INT_MIN, cg::greater<int>());
         const int v1 = cg::reduce(tile, member ? hi1 : INT_MIN, cg::greater<int>());
         const int v2 = cg::reduce(tile, member ? hi2 : INT_MIN, cg::greater<int>());
+        // cells of the previous round's box need no second visit (if it lies inside this one)
+        const bool skip_prev = w0 >= p0 && p0 >= u0 && w0 <= v0 && p1 >= u1 && w1 <= v1 && p2 >= u2 && w2 <= v2;
 
         // ---- visit every occupied cell of the union box [u, v] ----
         const int bx0 = u0 >> 2, by0 = u1 >> 2, bz0 = u2 >> 2;
@@ -95,13 +151,20 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
             if (b < nb) {
                 const int ix = b % nbx, t = b / nbx;
                 const int bx = bx0 + ix, by = by0 + t % nby, bz = bz0 + t / nby;
-                const uint4 rec = __ldg(Gv.bricks + ((size_t)bz * Gv.bny + by) * Gv.bnx + bx);
-                occ = ((unsigned long long)rec.y << 32) | rec.x;
-                if (occ) {
-                    const int x0 = max(u0 - bx * 4, 0), x1 = min(v0 - bx * 4, 3);
-                    const int y0 = max(u1 - by * 4, 0), y1 = min(v1 - by * 4, 3);
-                    const int z0 = max(u2 - bz * 4, 0), z1 = min(v2 - bz * 4, 3);
-                    m = occ & brick_box_mask(x0, x1, y0, y1, z0, z1);
+                const int x0 = max(u0 - bx * 4, 0), x1 = min(v0 - bx * 4, 3);
+                const int y0 = max(u1 - by * 4, 0), y1 = min(v1 - by * 4, 3);
+                const int z0 = max(u2 - bz * 4, 0), z1 = min(v2 - bz * 4, 3);
+                unsigned long long keep = brick_box_mask(x0, x1, y0, y1, z0, z1);
+                if (skip_prev) {
+                    const int a0 = max(p0 - bx * 4, 0), a1 = min(w0 - bx * 4, 3);
+                    const int b0_ = max(p1 - by * 4, 0), b1 = min(w1 - by * 4, 3);
+                    const int c0_ = max(p2 - bz * 4, 0), c1 = min(w2 - bz * 4, 3);
+                    if (a0 <= a1 && b0_ <= b1 && c0_ <= c1) keep &= ~brick_box_mask(a0, a1, b0_, b1, c0_, c1);
+                }
+                if (keep) {
+                    const uint4 rec = __ldg(Gv.bricks + ((size_t)bz * Gv.bny + by) * Gv.bnx + bx);
+                    occ = ((unsigned long long)rec.y << 32) | rec.x;
+                    m = occ & keep;
                     base = rec.z;
                 }
             }
@@ -147,6 +210,7 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
             }
         }
 
+        p0 = u0; p1 = u1; p2 = u2; w0 = v0; w1 = v1; w2 = v2;
         // ---- members decide whether they are finished ----
         if (member) {
             float bound = 3.0e38f;
@@ -159,7 +223,7 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
             if (v2 < Gv.cnz - 1) { bound = fminf(bound, (float)(v2 + 1) - gz); open = true; }
             bound -= Gv.slack;
             const float rad = sqrtf(best_d2) * Gv.inv_h;
-            if (!open || rad <= bound) {
+            if (!open || rad <= bound || (first_hit && best_pos >= 0)) {
                 pending = false;
             } else if (best_pos >= 0) {
                 const float r = rad * 1.000001f + Gv.slack;          // box enclosing the ball, merged with the visited box
@@ -177,6 +241,80 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
                 lo2 = max(u2 - ez, 0); hi2 = min(v2 + ez, Gv.cnz - 1);
             }
         }
+    }
+}
+
+// Exact search for lanes that already hold an upper bound (best_d2, best_pos >= 0): the tile
+// walks the bricks of the union of the lanes' ball boxes TOGETHER (uniform loop, broadcast brick
+// loads); inside a brick every lane pops the occupied cells of ITS OWN ball box, prunes them by
+// box distance against ITS OWN bound and evaluates the survivors -- different lanes work on
+// different cells in the same instruction, so pruned per-query work is packed across the warp
+// instead of being serialised (per-lane search) or multiplied by 32 (shared candidate list).
+template <int G>
+__device__ __forceinline__ void warp_pruned_search(const cg::thread_block_tile<G>& tile, const GridView& Gv, bool active,
+                                                   float qx, float qy, float qz, float& best_d2, int& best_pos) {
+    const float gx = (qx - Gv.ox) * Gv.inv_h, gy = (qy - Gv.oy) * Gv.inv_h, gz = (qz - Gv.oz) * Gv.inv_h;
+    const float r = sqrtf(best_d2) * Gv.inv_h * 1.000001f + Gv.slack;
+    const int lo0 = cell_clamped(gx - r, Gv.cnx), hi0 = cell_clamped(gx + r, Gv.cnx);
+    const int lo1 = cell_clamped(gy - r, Gv.cny), hi1 = cell_clamped(gy + r, Gv.cny);
+    const int lo2 = cell_clamped(gz - r, Gv.cnz), hi2 = cell_clamped(gz + r, Gv.cnz);
+    const float h2 = Gv.h * Gv.h;
+    bool pending = active;
+    for (;;) {
+        const unsigned act = tile.ballot(pending);
+        if (act == 0u) break;
+        const int leader = __ffs(act) - 1;
+        const int L0 = tile.shfl(lo0, leader), H0 = tile.shfl(hi0, leader);
+        const int L1 = tile.shfl(lo1, leader), H1 = tile.shfl(hi1, leader);
+        const int L2 = tile.shfl(lo2, leader), H2 = tile.shfl(hi2, leader);
+        const int gap = max(max(max(L0 - hi0, lo0 - H0), max(L1 - hi1, lo1 - H1)), max(L2 - hi2, lo2 - H2));
+        const bool member = pending && gap <= 4;
+        const int bx0 = cg::reduce(tile, member ? lo0 : INT_MAX, cg::less<int>()) >> 2;
+        const int by0 = cg::reduce(tile, member ? lo1 : INT_MAX, cg::less<int>()) >> 2;
+        const int bz0 = cg::reduce(tile, member ? lo2 : INT_MAX, cg::less<int>()) >> 2;
+        const int bx1 = cg::reduce(tile, member ? hi0 : INT_MIN, cg::greater<int>()) >> 2;
+        const int by1 = cg::reduce(tile, member ? hi1 : INT_MIN, cg::greater<int>()) >> 2;
+        const int bz1 = cg::reduce(tile, member ? hi2 : INT_MIN, cg::greater<int>()) >> 2;
+        for (int bz = bz0; bz <= bz1; ++bz)
+            for (int by = by0; by <= by1; ++by)
+                for (int bx = bx0; bx <= bx1; ++bx) {
+                    const uint4 rec = __ldg(Gv.bricks + ((size_t)bz * Gv.bny + by) * Gv.bnx + bx);   // same address in every lane
+                    const unsigned long long occ = ((unsigned long long)rec.y << 32) | rec.x;
+                    if (occ == 0ull) continue;
+                    unsigned long long m = 0ull;
+                    if (member) {
+                        const int x0 = max(lo0 - bx * 4, 0), x1 = min(hi0 - bx * 4, 3);
+                        const int y0 = max(lo1 - by * 4, 0), y1 = min(hi1 - by * 4, 3);
+                        const int z0 = max(lo2 - bz * 4, 0), z1 = min(hi2 - bz * 4, 3);
+                        if (x0 <= x1 && y0 <= y1 && z0 <= z1) m = occ & brick_box_mask(x0, x1, y0, y1, z0, z1);
+                    }
+                    while (tile.any(m != 0ull)) {
+                        uint32_t s = 0u, len = 0u;
+                        if (m != 0ull) {
+                            const int bit = __ffsll((long long)m) - 1;
+                            m &= m - 1ull;
+                            const int cx = bx * 4 + (bit & 3), cy = by * 4 + ((bit >> 2) & 3), cz = bz * 4 + (bit >> 4);
+                            const float dx = fmaxf(fmaxf((float)cx - gx, gx - (float)(cx + 1)) - Gv.slack, 0.0f);
+                            const float dy = fmaxf(fmaxf((float)cy - gy, gy - (float)(cy + 1)) - Gv.slack, 0.0f);
+                            const float dz = fmaxf(fmaxf((float)cz - gz, gz - (float)(cz + 1)) - Gv.slack, 0.0f);
+                            if ((dx * dx + dy * dy + dz * dz) * h2 < best_d2) {
+                                const uint32_t ord = rec.z + (uint32_t)__popcll(occ & ((1ull << bit) - 1ull));
+                                s = __ldg(Gv.cell_start + ord);
+                                len = __ldg(Gv.cell_start + ord + 1) - s;
+                            }
+                        }
+                        const uint32_t maxlen = cg::reduce(tile, len, cg::greater<uint32_t>());
+                        for (uint32_t k = 0; k < maxlen; ++k) {
+                            if (k < len) {
+                                const float4 t = __ldg(Gv.pts + s + k);
+                                const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+                                const float d2 = ex * ex + ey * ey + ez * ez;
+                                if (d2 < best_d2) { best_d2 = d2; best_pos = (int)(s + k); }
+                            }
+                        }
+                    }
+                }
+        if (member) pending = false;
     }
 }
 
