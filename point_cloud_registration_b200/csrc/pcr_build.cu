@@ -714,7 +714,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
         const int g = atoi(e);
         ctx->tile_lanes = g == 32 ? 32 : 0;
     }
-    if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) == 3 ? 3 : 2;
+    if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
     if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 24.0;
     if (const char* e = getenv("PCR_R0_MIN")) ctx->r0_min = (float)atof(e);
     if (const char* e = getenv("PCR_WARM")) ctx->warm_start = atoi(e);

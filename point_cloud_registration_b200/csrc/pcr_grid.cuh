@@ -185,7 +185,7 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
     cur.x0 = cur.x1 = cell_of(cgx, G.cnx);
     cur.y0 = cur.y1 = cell_of(cgy, G.cny);
     cur.z0 = cur.z1 = cell_of(cgz, G.cnz);
-    visit_block(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+    visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
     for (;;) {
         // distance (grid units) from the query to the nearest face of the visited block that
         // still has unvisited grid cells behind it
@@ -218,7 +218,8 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
         nb.x0 = cur.x0 > 0 ? cur.x0 - 1 : 0; nb.x1 = cur.x1 < G.cnx - 1 ? cur.x1 + 1 : cur.x1;
         nb.y0 = cur.y0 > 0 ? cur.y0 - 1 : 0; nb.y1 = cur.y1 < G.cny - 1 ? cur.y1 + 1 : cur.y1;
         nb.z0 = cur.z0 > 0 ? cur.z0 - 1 : 0; nb.z1 = cur.z1 < G.cnz - 1 ? cur.z1 + 1 : cur.z1;
-        visit_block(G, qx, qy, qz, gx, gy, gz, nb, cur, true, best);
+        if (is_small_box(nb)) visit_small_box(G, qx, qy, qz, gx, gy, gz, nb, cur, true, best);
+        else visit_block(G, qx, qy, qz, gx, gy, gz, nb, cur, true, best);
         cur = nb;
     }
 }

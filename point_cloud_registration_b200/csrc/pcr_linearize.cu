@@ -21,10 +21,6 @@
 #include "pcr_terms.cuh"
 #include "pcr_tile_search.cuh"
 
-#ifndef PCR_LANE_MINB
-#define PCR_LANE_MINB 2
-#endif
-
 namespace pcr {
 
 struct LinParams {
@@ -240,29 +236,40 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_tile_kernel(const
 }
 
 // ---- variant B: independent per-lane search (any scan order) -----------------------------------
-template <int METHOD>
-__global__ void __launch_bounds__(kLinThreads, PCR_LANE_MINB) linearize_lane_kernel(const LinParams P) {
+// Two passes over the thread's own points keep the register footprint at max(search,
+// accumulate) instead of their sum: pass 1 searches and parks the matched position in P.prev
+// (4 B/point, L2-resident), pass 2 re-reads it, gathers the record and accumulates.
+template <int METHOD, int MINB>
+__global__ void __launch_bounds__(kLinThreads, MINB) linearize_lane_kernel(const LinParams P) {
     constexpr int NACC = NAcc<METHOD>::value;
     __shared__ BlockShared sh;
     Pose32 pose;
     float r0;
     if (!load_pose(P, sh, pose, r0)) return;
-
-    float acc[NACC + 1];
-#pragma unroll
-    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
     const long long stride = (long long)gridDim.x * kLinThreads;
-    for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride) {
+    const long long first = blockIdx.x * (long long)kLinThreads + threadIdx.x;
+
+    for (long long i = first; i < P.n_pad; i += stride) {
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
         float d2;
-        const int pos = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? __ldg(P.prev + i) : -1, d2);
-        P.prev[i] = pos;
-        if (pos >= 0) {
-            accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
-            acc[NACC] += sqrtf(d2);
-        }
+        P.prev[i] = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? P.prev[i] : -1, d2);
+    }
+
+    float acc[NACC + 1];
+#pragma unroll
+    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
+    for (long long i = first; i < P.n_pad; i += stride) {
+        const int pos = P.prev[i];                       // written by this very thread in pass 1
+        if (pos < 0) continue;
+        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+        float qx, qy, qz;
+        transform32(pose, px, py, pz, qx, qy, qz);
+        accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
+        const float4 t = __ldg(P.grid.pts + pos);
+        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+        acc[NACC] += sqrtf(ex * ex + ey * ey + ez * ez);
     }
     reduce_and_finish<METHOD>(P, sh, acc);
 }
@@ -528,15 +535,27 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     // variant: tile-cooperative search for spatially sorted scans, per-lane search otherwise
     // (sub-warp tiles were measured and rejected: the tiles of one warp diverge from each other,
     //  so their costs add up instead of overlapping -- profiles/r1_notes.md)
-    const int v = (ctx->scan_sorted && ctx->tile_lanes == 32) ? (ctx->min_blocks == 3 ? 2 : 1) : 0;
+    const bool tile = ctx->scan_sorted && ctx->tile_lanes == 32;
+    const int mb = ctx->min_blocks;                       // 2, 3 or 4 resident blocks per SM requested
+    const int v = tile ? (mb >= 3 ? 1 : 0) : (mb >= 4 ? 4 : (mb == 3 ? 3 : 2));
     int& per_sm = ctx->lin_blocks_per_sm[METHOD][v];
-    if (per_sm == 0)
-        per_sm = v == 2 ? blocks_per_sm(linearize_tile_kernel<METHOD, 32, 3>)
-                        : (v == 1 ? blocks_per_sm(linearize_tile_kernel<METHOD, 32, 2>) : blocks_per_sm(linearize_lane_kernel<METHOD>));
+    if (per_sm == 0) {
+        switch (v) {
+            case 0: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 32, 2>); break;
+            case 1: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 32, 3>); break;
+            case 2: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 2>); break;
+            case 3: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 3>); break;
+            default: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 4>); break;
+        }
+    }
     const int blocks = lin_grid_blocks(ctx, P.n_pad, per_sm);
-    if (v == 2) linearize_tile_kernel<METHOD, 32, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
-    else if (v == 1) linearize_tile_kernel<METHOD, 32, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
-    else linearize_lane_kernel<METHOD><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
+    switch (v) {
+        case 0: linearize_tile_kernel<METHOD, 32, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 1: linearize_tile_kernel<METHOD, 32, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 2: linearize_lane_kernel<METHOD, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 3: linearize_lane_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        default: linearize_lane_kernel<METHOD, 4><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+    }
     PCR_LAUNCH_CHECK();
     return PCR_OK;
 }

@@ -20,6 +20,7 @@ class Registration:
         self._is_target_set = False
         self._ctx = None
         self._dist = None          # (rank, world_size) once attach_communicator() was called
+        self.scan_is_presharded = False   # multi-GPU: scans passed in are already this rank's tile
         self.sort_scan = True      # Morton-sort the scan on upload in align()
         self.last_iterations = 0
         self.last_e2_trace = None
@@ -94,7 +95,7 @@ class Registration:
         if self._ctx is None:
             raise ValueError("Target is not set.")
         src = _lib.as_f32_points(source, "source")               # registration.py:83
-        if self._dist is not None:
+        if self._dist is not None and not self.scan_is_presharded:
             from .distributed import shard_bounds
             lo, hi = shard_bounds(src.shape[0], *self._dist)
             src = src[lo:hi]
