@@ -97,6 +97,8 @@ class DevicePoints:
     device pointer -- no host round trip."""
 
     def __init__(self, obj, name="points"):
+        if isinstance(obj, DevicePoints):
+            obj = obj.obj
         cai = obj.__cuda_array_interface__
         shape, typestr = tuple(cai["shape"]), cai["typestr"]
         if len(shape) != 2 or shape[1] != 3:
@@ -116,7 +118,7 @@ class DevicePoints:
 
 
 def is_device_array(a):
-    return hasattr(a, "__cuda_array_interface__")
+    return isinstance(a, DevicePoints) or hasattr(a, "__cuda_array_interface__")
 
 
 def _ptr(a):
