@@ -198,18 +198,13 @@ def workload_config(wl_name, wl, world, n_total):
 # ----------------------------------------------------------------------------------------------
 # B200 arm
 # ----------------------------------------------------------------------------------------------
-def run_b200(args, wl_name, wl, world, rank, local_rank):
+def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, light=False):
     import torch
     import point_cloud_registration_b200 as pcr
     from point_cloud_registration_b200 import _lib, datasets as ds
     from point_cloud_registration_b200.distributed import shard_bounds
 
-    torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=dev)
 
     n_total = wl["n"] * (world if wl_name == "c5" else 1)
     cls = getattr(pcr, wl["cls"])
@@ -266,7 +261,7 @@ def run_b200(args, wl_name, wl, world, rank, local_rank):
 
     # ---- parity vs the CPU oracle + cpu_baseline (rank 0, single GPU, host workload) ---------
     transform_err, cpu_baseline = None, None
-    if world == 1 and rank == 0 and not args.no_cpu:
+    if world == 1 and rank == 0 and not args.no_cpu and not light:
         cores = os.cpu_count()
         if on_host:
             t0 = time.perf_counter()
@@ -300,7 +295,8 @@ def run_b200(args, wl_name, wl, world, rank, local_rank):
     # ---- timed region 1: device-resident iterations, per-iteration CUDA events ----------------
     ext = torch.cuda.ExternalStream(ctx.stream(), device=dev)
     flush = torch.empty(512 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    K, W = args.steps, args.warmup
+    K, W = (min(args.steps, 40), min(args.warmup, 5)) if light else (args.steps, args.warmup)
+    W = ((W + m - 1) // m) * m            # whole align() trajectories: timed step j is iteration j % m
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -359,6 +355,8 @@ def run_b200(args, wl_name, wl, world, rank, local_rank):
 
     # ---- timed region 3: end to end through the Python class with host buffers ------------------
     Ke = K if wl_name == "c2" else max(3, min(K, 20))
+    if light:
+        Ke = 5
     barrier()
     for i in range(min(W, 3) + Ke):
         if i == min(W, 3):
@@ -402,7 +400,7 @@ def run_b200(args, wl_name, wl, world, rank, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_scan_point": wl["bytes_per_point"],
-                         "kernel": f"linearize_kernel<{wl['cls']}> (fused transform+NN+residual+reduce+GN step)"},
+                         "kernel": f"linearize_lane_kernel<{wl['cls']}> (fused transform + exact NN + residual/Jacobian + reduction + GN step)"},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches),
@@ -410,17 +408,18 @@ def run_b200(args, wl_name, wl, world, rank, local_rank):
             "warm_l2": warm,
             "transform_err_vs_ref": transform_err,
             "align_iterations": m,
-            "step_ms_by_iteration": [float(step_ms[j::m].mean()) for j in range(m)] if (W % m == 0 and K >= m) else None,
+            "step_ms_by_iteration": [float(step_ms[j::m].mean()) for j in range(m)] if K >= m else None,
             "tile_lanes": os.environ.get("PCR_TILE_LANES", "default"),
             "set_target_s": set_target_s, "scan_upload_sort_ms": set_scan_s * 1e3,
             "wall_ms_per_step_incl_flush": wall_s * 1e3 / K,
             "points_per_sec": value * n_total,
             "nn_index": stats,
         }
-        print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
+    else:
+        line = None
+    del reg, ctx, handle, flush
+    torch.cuda.empty_cache()
+    return line
 
 
 def main():
@@ -431,6 +430,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="auto", choices=["auto", "c2", "c3", "c4", "c5"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the oracle parity / cpu_baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the shortened c3/c4 context runs of the default invocation")
     args = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -442,8 +442,32 @@ def main():
     wl = WORKLOADS[wl_name]
     if args.impl == "reference":
         run_reference(args, wl_name, wl, world, rank)
-    else:
-        run_b200(args, wl_name, wl, world, rank, local_rank)
+        return
+    import torch
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_b200(args, wl_name, wl, world, rank, local_rank, dist)
+    if world == 1 and args.workload == "auto" and not args.no_others:
+        # the other single-GPU configurations of BASELINE.json, shortened, for context
+        others = []
+        for name in ("c3", "c4"):
+            try:
+                o = run_b200(args, name, WORKLOADS[name], world, rank, local_rank, dist, light=True)
+                others.append({k: o[k] for k in ("value", "unit", "ms_per_step", "steps", "step_ms_by_iteration", "align_iterations",
+                                                 "set_target_s", "points_per_sec")} |
+                              {"workload": o["config"]["workload"], "roofline_frac": o["roofline"]["frac"],
+                               "achieved_GBps": o["roofline"]["achieved"], "e2e_value": o["e2e"]["value"], "warm_l2_value": o["warm_l2"]["value"]})
+            except Exception as e:            # context only: never lose the main line
+                others.append({"workload": name, "error": repr(e)})
+        line["other_workloads"] = others
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -172,6 +172,10 @@ int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max
  * warp-cooperative search for sorted scans (kept for A/B measurements; slower on the measured
  * workloads, see profiles/).  Also settable at context creation through PCR_TILE_LANES. */
 int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes);
+/* Voxel-mean correspondences are read from exact per-cell candidate lists built with the voxels
+ * (default on); 0 falls back to the general grid search everywhere (A/B and test hook). */
+int pcr_set_voxel_lists(pcr_ctx* ctx, int enable);
+int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
 /* Test hook: exact NN of every resident scan point (storage order; upload with sort <= 0 to keep
  * the caller's order) under transform T through the TILE-COOPERATIVE search, against the target
  * points (which = 0) or the kept voxel means (which = 1); r0 = first search radius in cells.

@@ -54,6 +54,8 @@ SYMBOLS = {
     "pcr_stream": (_i, [_vp, C.POINTER(_vp)]),
     "pcr_linearize_async": (_i, [_vp, _i, _vp, _d, _i]),
     "pcr_set_tile_lanes": (_i, [_vp, _i]),
+    "pcr_set_voxel_lists": (_i, [_vp, _i]),
+    "pcr_voxel_list_stats": (_i, [_vp, _pi64, _pi64]),
     "pcr_debug_tile_nn": (_i, [_vp, _i, _vp, _d, _d, _vp, _vp]),
     "pcr_index_stats": (_i, [_vp, _i, C.POINTER(_d), _pi64, _pi64, _pi64]),
 }
@@ -234,6 +236,14 @@ class Context:
         """sort: True/1 Morton-sort on the device; False/0 keep order (per-point search);
         -1 keep order, caller promises spatial coherence (tile-cooperative search)."""
         self._check(self._lib.pcr_set_scan(self._h, _ptr(pts_f32), pts_f32.shape[0], int(sort)))
+
+    def set_voxel_lists(self, enable):
+        self._check(self._lib.pcr_set_voxel_lists(self._h, int(bool(enable))))
+
+    def voxel_list_stats(self):
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._lib.pcr_voxel_list_stats(self._h, C.byref(a), C.byref(b)))
+        return dict(band_cells=a.value, entries=b.value)
 
     def set_tile_lanes(self, lanes):
         self._check(self._lib.pcr_set_tile_lanes(self._h, int(lanes)))

@@ -491,13 +491,14 @@ __global__ void voxel_centroid_kernel(const double* __restrict__ mean_all, uint3
     out[3 * (size_t)v + 2] = (float)mean_all[3 * (size_t)v + 2];
 }
 
-__global__ void voxel_query_kernel(GridView G, const float* __restrict__ q, long long m, const double* __restrict__ mean,
-                                   long long* __restrict__ vidx, double* __restrict__ dist) {
+__global__ void voxel_query_kernel(GridView G, CandLists L, int use_lists, const float* __restrict__ q, long long m,
+                                   const double* __restrict__ mean, long long* __restrict__ vidx, double* __restrict__ dist) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= m) return;
     float d2;
     const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-    const int pos = grid_nn(G, qx, qy, qz, 3.0e38f, d2);
+    int pos;
+    if (!(use_lists && list_nn(G, L, qx, qy, qz, 3.0e38f, d2, pos))) pos = grid_nn(G, qx, qy, qz, 3.0e38f, d2);
     if (pos >= 0) {
         const size_t o = __float_as_uint(G.pts[pos].w);
         const double dx = (double)qx - mean[3 * o], dy = (double)qy - mean[3 * o + 1], dz = (double)qz - mean[3 * o + 2];
@@ -587,6 +588,167 @@ static int voxel_front(pcr_ctx* ctx, const void* xyz, long long n, double voxel_
     return PCR_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------
+// per-cell candidate lists over the kept voxel means (see CandLists in pcr_common.cuh)
+// ---------------------------------------------------------------------------------------
+constexpr int kBandDilate = 2;     // cells within this Chebyshev distance of a kept voxel get a list
+constexpr int kListRadius = 3;     // list build looks at the (2R+1)^3 neighbourhood; exact while D_C < R
+
+// mark the neighbourhood of every kept voxel as "band" (cells that get a list)
+__global__ void band_mark_kernel(GridView G, BrickRec* __restrict__ lbricks) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= G.n_pts) return;
+    const float4 m = G.pts[v];
+    const int cx = cell_of((m.x - G.ox) * G.inv_h, G.cnx), cy = cell_of((m.y - G.oy) * G.inv_h, G.cny), cz = cell_of((m.z - G.oz) * G.inv_h, G.cnz);
+    const int x0 = max(cx - kBandDilate, 0), x1 = min(cx + kBandDilate, G.cnx - 1);
+    const int y0 = max(cy - kBandDilate, 0), y1 = min(cy + kBandDilate, G.cny - 1);
+    const int z0 = max(cz - kBandDilate, 0), z1 = min(cz + kBandDilate, G.cnz - 1);
+    for (int bz = z0 >> 2; bz <= z1 >> 2; ++bz)
+        for (int by = y0 >> 2; by <= y1 >> 2; ++by)
+            for (int bx = x0 >> 2; bx <= x1 >> 2; ++bx) {
+                const unsigned long long mk = brick_box_mask(max(x0 - bx * 4, 0), min(x1 - bx * 4, 3), max(y0 - by * 4, 0), min(y1 - by * 4, 3),
+                                                             max(z0 - bz * 4, 0), min(z1 - bz * 4, 3));
+                BrickRec* r = &lbricks[((size_t)bz * G.bny + by) * G.bnx + bx];
+                if ((r->mask & mk) != mk) atomicOr(&r->mask, mk);
+            }
+}
+
+__global__ void brick_popc_kernel(const BrickRec* __restrict__ bricks, unsigned long long n, uint32_t* __restrict__ cnt) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) cnt[i] = (uint32_t)__popcll(bricks[i].mask);
+}
+
+__global__ void brick_base_set_kernel(BrickRec* __restrict__ bricks, unsigned long long n, const uint32_t* __restrict__ base) {
+    unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i < n) bricks[i].base = base[i];
+}
+
+// One thread per (brick, bit) of the band.  FILL = false: D2[ordinal] = D_C^2 (or -1: no list) and
+// counts[ordinal] = list length; FILL = true: write the list.  The neighbourhood is walked brick
+// by brick through the occupancy masks, so empty cells cost nothing.
+template <bool FILL>
+__global__ void list_build_kernel(GridView G, const BrickRec* __restrict__ lbricks, unsigned long long nbricks, float* __restrict__ D2s,
+                                  uint32_t* __restrict__ counts, const uint32_t* __restrict__ list_start, uint32_t* __restrict__ list_idx) {
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long b = tid >> 6;
+    const int bit = (int)(tid & 63ull);
+    if (b >= nbricks) return;
+    const BrickRec lr = lbricks[b];
+    if (!((lr.mask >> bit) & 1ull)) return;
+    const uint32_t ord = lr.base + (uint32_t)__popcll(lr.mask & ((1ull << bit) - 1ull));
+    const int bx = (int)(b % (unsigned long long)G.bnx), by = (int)((b / (unsigned long long)G.bnx) % (unsigned long long)G.bny),
+              bz = (int)(b / ((unsigned long long)G.bnx * G.bny));
+    const int cx = bx * 4 + (bit & 3), cy = by * 4 + ((bit >> 2) & 3), cz = bz * 4 + (bit >> 4);
+    const float fx = (float)cx, fy = (float)cy, fz = (float)cz;
+    const int x0 = max(cx - kListRadius, 0), x1 = min(cx + kListRadius, G.cnx - 1);
+    const int y0 = max(cy - kListRadius, 0), y1 = min(cy + kListRadius, G.cny - 1);
+    const int z0 = max(cz - kListRadius, 0), z1 = min(cz + kListRadius, G.cnz - 1);
+    float D2 = FILL ? D2s[ord] : 3.0e38f;
+    if (FILL && D2 < 0.f) return;
+    for (int pass = FILL ? 1 : 0; pass < 2; ++pass) {
+        float lim2 = 0.f;
+        uint32_t n_out = 0, w = 0;
+        if (pass == 1) {
+            const float D = sqrtf(D2);
+            if (!FILL && !(D < (float)kListRadius - 2.0f * G.slack)) {   // neighbourhood too small to be exact here: no list
+                D2s[ord] = -1.0f;
+                counts[ord] = 0u;
+                return;
+            }
+            lim2 = (D + G.slack) * (D + G.slack);
+            if (FILL) w = list_start[ord];
+        }
+        for (int nz = z0 >> 2; nz <= z1 >> 2; ++nz)
+            for (int ny = y0 >> 2; ny <= y1 >> 2; ++ny)
+                for (int nx = x0 >> 2; nx <= x1 >> 2; ++nx) {
+                    const uint4 rec = G.bricks[((size_t)nz * G.bny + ny) * G.bnx + nx];
+                    const unsigned long long occ = ((unsigned long long)rec.y << 32) | rec.x;
+                    if (occ == 0ull) continue;
+                    unsigned long long m = occ & brick_box_mask(max(x0 - nx * 4, 0), min(x1 - nx * 4, 3), max(y0 - ny * 4, 0), min(y1 - ny * 4, 3),
+                                                                max(z0 - nz * 4, 0), min(z1 - nz * 4, 3));
+                    while (m) {
+                        const int nb = __ffsll((long long)m) - 1;
+                        m &= m - 1ull;
+                        const uint32_t o2 = rec.z + (uint32_t)__popcll(occ & ((1ull << nb) - 1ull));
+                        const uint32_t s = G.cell_start[o2], e = G.cell_start[o2 + 1];
+                        for (uint32_t p = s; p < e; ++p) {
+                            const float4 mp = G.pts[p];
+                            const float gx = (mp.x - G.ox) * G.inv_h, gy = (mp.y - G.oy) * G.inv_h, gz = (mp.z - G.oz) * G.inv_h;
+                            if (pass == 0) {
+                                const float ax = fmaxf(fabsf(gx - fx), fabsf(gx - fx - 1.0f));
+                                const float ay = fmaxf(fabsf(gy - fy), fabsf(gy - fy - 1.0f));
+                                const float az = fmaxf(fabsf(gz - fz), fabsf(gz - fz - 1.0f));
+                                D2 = fminf(D2, ax * ax + ay * ay + az * az);
+                            } else {
+                                const float ax = fmaxf(fmaxf(fx - gx, gx - fx - 1.0f), 0.0f);
+                                const float ay = fmaxf(fmaxf(fy - gy, gy - fy - 1.0f), 0.0f);
+                                const float az = fmaxf(fmaxf(fz - gz, gz - fz - 1.0f), 0.0f);
+                                if (ax * ax + ay * ay + az * az <= lim2) {
+                                    if (FILL) list_idx[w++] = p;
+                                    ++n_out;
+                                }
+                            }
+                        }
+                    }
+                }
+        if (pass == 1 && !FILL) { counts[ord] = n_out; D2s[ord] = D2; }
+    }
+}
+
+static int build_voxel_lists(pcr_ctx* ctx) {
+    Grid& g = ctx->vox_grid;
+    ctx->vox_lists = CandLists{};
+    ctx->n_band_cells = ctx->n_list_entries = 0;
+    if (!g.built || g.view.n_pts == 0) return PCR_OK;
+    if (const char* e = getenv("PCR_VOXEL_LISTS")) if (atoi(e) == 0) return PCR_OK;
+    const GridView& G = g.view;
+    const unsigned long long nbricks = (unsigned long long)G.bnx * G.bny * G.bnz;
+    PCR_CUDA(ctx->vox_lbricks.ensure((size_t)nbricks * sizeof(BrickRec)));
+    PCR_CUDA(cudaMemsetAsync(ctx->vox_lbricks.p, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
+    BrickRec* lb = ctx->vox_lbricks.as<BrickRec>();
+    band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb);
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(ctx->tmp_a.ensure((size_t)(nbricks + 1) * 4 * 2));
+    uint32_t* bcnt = ctx->tmp_a.as<uint32_t>();
+    uint32_t* bbase = bcnt + (nbricks + 1);
+    PCR_CUDA(cudaMemsetAsync(bcnt, 0, (size_t)(nbricks + 1) * 4, ctx->stream));
+    brick_popc_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bcnt);
+    PCR_LAUNCH_CHECK();
+    int rc = exclusive_sum_u32(ctx, bcnt, bbase, (long long)nbricks + 1);
+    if (rc) return rc;
+    uint32_t n_band = 0;
+    PCR_CUDA(cudaMemcpyAsync(&n_band, bbase + nbricks, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    brick_base_set_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bbase);
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(ctx->tmp_b.ensure(((size_t)n_band + 1) * 4));
+    PCR_CUDA(ctx->tmp_c.ensure(((size_t)n_band + 1) * 4));
+    PCR_CUDA(ctx->vox_list_start.ensure(((size_t)n_band + 1) * 4));
+    uint32_t* counts = ctx->tmp_b.as<uint32_t>();
+    float* D2s = ctx->tmp_c.as<float>();
+    PCR_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_band + 1) * 4, ctx->stream));
+    const long long nthreads = (long long)nbricks * 64;
+    list_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, counts, nullptr, nullptr);
+    PCR_LAUNCH_CHECK();
+    rc = exclusive_sum_u32(ctx, counts, ctx->vox_list_start.as<uint32_t>(), (long long)n_band + 1);
+    if (rc) return rc;
+    uint32_t n_entries = 0;
+    PCR_CUDA(cudaMemcpyAsync(&n_entries, ctx->vox_list_start.as<uint32_t>() + n_band, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    PCR_CUDA(ctx->vox_list_idx.ensure(((size_t)n_entries + 1) * 4));
+    list_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, nullptr, ctx->vox_list_start.as<uint32_t>(),
+                                                                               ctx->vox_list_idx.as<uint32_t>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->vox_lists.bricks = ctx->vox_lbricks.as<uint4>();
+    ctx->vox_lists.list_start = ctx->vox_list_start.as<uint32_t>();
+    ctx->vox_lists.list_idx = ctx->vox_list_idx.as<uint32_t>();
+    ctx->n_band_cells = n_band;
+    ctx->n_list_entries = n_entries;
+    return PCR_OK;
+}
+
 template <typename T>
 static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double voxel_size, int min_points, int with_icov) {
     VoxelFront F;
@@ -644,6 +806,8 @@ static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     g.built = true;
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     F.release();
+    rc = build_voxel_lists(ctx);
+    if (rc) return rc;
     ctx->has_voxels = true;
     ctx->has_icov = with_icov != 0;
     return PCR_OK;
@@ -735,6 +899,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->tgt_xyz.release(); ctx->tgt_grid.release(); ctx->tgt_nrm_sorted.release(); ctx->tgt_nrm_orig.release();
     ctx->vox_mean.release(); ctx->vox_cov.release(); ctx->vox_norm.release(); ctx->vox_icov.release(); ctx->vox_count.release();
     ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
+    ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release();
     ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();
     ctx->partials.release(); ctx->state.release();
     ctx->tmp_a.release(); ctx->tmp_b.release(); ctx->tmp_c.release(); ctx->tmp_d.release(); ctx->tmp_e.release(); ctx->cub_tmp.release();
@@ -895,8 +1060,9 @@ int pcr_voxel_query(pcr_ctx* ctx, const float* queries, int64_t m, int64_t* vidx
     }
     PCR_CUDA(dd.ensure((size_t)m * 8));
     PCR_CUDA(di.ensure((size_t)m * 8));
-    voxel_query_kernel<<<blocks_for(m, 128), 128, 0, ctx->stream>>>(ctx->vox_grid.view, q, m, ctx->vox_mean.as<double>(),
-                                                                    di.as<long long>(), dd.as<double>());
+    voxel_query_kernel<<<blocks_for(m, 128), 128, 0, ctx->stream>>>(ctx->vox_grid.view, ctx->vox_lists,
+                                                                    ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr, q, m,
+                                                                    ctx->vox_mean.as<double>(), di.as<long long>(), dd.as<double>());
     PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaMemcpyAsync(vidx, di.p, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
@@ -923,6 +1089,19 @@ int pcr_index_stats(pcr_ctx* ctx, int which, double* cell_edge, int64_t* n_cells
     if (n_cells) *n_cells = g.n_cells;
     if (n_bricks) *n_bricks = (int64_t)g.view.bnx * g.view.bny * g.view.bnz;
     if (n_points) *n_points = g.view.n_pts;
+    return PCR_OK;
+}
+
+int pcr_set_voxel_lists(pcr_ctx* ctx, int enable) {
+    if (!ctx) return PCR_ERR_ARG;
+    ctx->use_voxel_lists = enable ? 1 : 0;
+    return PCR_OK;
+}
+
+int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (band_cells) *band_cells = ctx->n_band_cells;
+    if (entries) *entries = ctx->n_list_entries;
     return PCR_OK;
 }
 

@@ -133,6 +133,21 @@ struct GridView {
     uint32_t n_pts;
 };
 
+// Per-cell exact candidate lists over a brick grid whose cells hold at most one point (the kept
+// voxel means): for every "band" cell C near a point, the list holds every indexed point that can
+// be the nearest neighbour of SOME location inside C:
+//     K_C = { m : mindist(C, m) <= D_C },   D_C = min_m maxdist(C, m)
+// (any query in C has its nearest neighbour within D_C, and that neighbour is at least
+// mindist(C, .) away).  A query only evaluates the list of its own cell -- no search -- and all
+// queries of one cell read the same addresses.  Cells without a list (far from every point, or
+// D_C >= 2 cells so that the 5x5x5 build neighbourhood would not suffice) fall back to the
+// general search.
+struct CandLists {
+    const uint4* bricks;         // (band mask lo, hi, ordinal of first band cell, unused), same brick layout as the grid
+    const uint32_t* list_start;  // [n_band + 1]
+    const uint32_t* list_idx;    // positions in GridView::pts
+};
+
 PCR_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 PCR_HD int cell_of(float g, int n) {          // grid coordinate -> clamped cell index

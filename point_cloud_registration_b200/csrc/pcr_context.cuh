@@ -76,6 +76,10 @@ struct pcr_ctx {
     double voxel_size = 0.0;
     pcr::DevBuf vox_mean, vox_cov, vox_norm, vox_icov, vox_count;   // double[3n], [9n], [3n], [9n], int64[n]
     pcr::Grid vox_grid;           // NN index over kept voxel means (payload = voxel ordinal)
+    pcr::DevBuf vox_lbricks, vox_list_start, vox_list_idx;   // per-cell candidate lists over the voxel means
+    pcr::CandLists vox_lists{};   // null pointers = not built
+    long long n_band_cells = 0, n_list_entries = 0;
+    int use_voxel_lists = 1;
     pcr::DevBuf vox_rec_plane;    // float4[2n]: (mean, 0), (normal, 0)
     pcr::DevBuf vox_rec_ndt;      // float4[3n]: (mean, W00), (W01, W02, W11, W12), (W22, 0, 0, 0)
     bool has_voxels = false, has_icov = false;

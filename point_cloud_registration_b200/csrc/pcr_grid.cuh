@@ -232,6 +232,34 @@ PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2
     return b.pos;
 }
 
+// 1-NN through the per-cell candidate lists (see CandLists); returns false when the query's cell
+// has no list and the caller must run the general search.
+PCR_HD bool list_nn(const GridView& G, const CandLists& L, float qx, float qy, float qz, float max_d2,
+                    float& out_d2, int& out_pos) {
+    const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
+    if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) return false;
+    const int cx = (int)gx, cy = (int)gy, cz = (int)gz;
+    const uint4 rec = L.bricks[((size_t)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2)];
+    const unsigned long long band = ((unsigned long long)rec.y << 32) | rec.x;
+    const int bit = brick_bit(cx, cy, cz);
+    if (!((band >> bit) & 1ull)) return false;
+    const uint32_t ord = rec.z + (uint32_t)popc64(band & ((1ull << bit) - 1ull));
+    const uint32_t s = L.list_start[ord], e = L.list_start[ord + 1];
+    if (s == e) return false;
+    float best = max_d2;
+    int pos = -1;
+    for (uint32_t k = s; k < e; ++k) {
+        const uint32_t p = L.list_idx[k];
+        const float4 t = G.pts[p];
+        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+        const float d2 = ex * ex + ey * ey + ez * ez;
+        if (d2 < best) { best = d2; pos = (int)p; }
+    }
+    out_d2 = best;
+    out_pos = pos;
+    return true;
+}
+
 // 1-NN with a warm start: `warm_pos` is the position of any indexed point (e.g. the previous
 // iteration's match, -1 = none); its distance bounds the search.
 PCR_HD int grid_nn_warm(const GridView& G, float qx, float qy, float qz, float max_d2, int warm_pos, float& out_d2) {

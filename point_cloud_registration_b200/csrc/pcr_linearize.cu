@@ -29,6 +29,8 @@ struct LinParams {
     GridView grid;                                       // target points (ICP/PLANE) or voxel means (VPLANE/NDT)
     const float4* nrm;                                   // PLANE: normals in grid order
     const float4* vrec;                                  // VPLANE: 2 float4 / voxel, NDT: 3 float4 / voxel
+    CandLists lists;                                     // VPLANE/NDT: per-cell candidate lists (null = absent)
+    int use_lists;
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
     float local_r1, local_r2; // mode 1: warm-start radius (cells) up to which the per-lane local search is used
@@ -254,7 +256,14 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_lane_kernel(const
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
         float d2;
-        P.prev[i] = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? P.prev[i] : -1, d2);
+        int pos;
+        if ((METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT) && P.use_lists) {
+            // voxel means: the query's cell carries the exact candidate list -- no search
+            if (!list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos)) pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+        } else {
+            pos = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? P.prev[i] : -1, d2);
+        }
+        P.prev[i] = pos;
     }
 
     float acc[NACC + 1];
@@ -517,6 +526,8 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.grid = (method == PCR_ICP || method == PCR_PLANE) ? ctx->tgt_grid.view : ctx->vox_grid.view;
     P.nrm = ctx->tgt_nrm_sorted.as<float4>();
     P.prev = ctx->scan_prev.as<int>();
+    P.lists = ctx->vox_lists;
+    P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
     P.local_r1 = ctx->local_r1;
     P.local_r2 = ctx->local_r2;
     P.search_mode = ctx->search_mode;
