@@ -882,9 +882,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 24.0;
     if (const char* e = getenv("PCR_R0_MIN")) ctx->r0_min = (float)atof(e);
     if (const char* e = getenv("PCR_WARM")) ctx->warm_start = atoi(e);
-    if (const char* e = getenv("PCR_SEARCH_MODE")) ctx->search_mode = atoi(e);
     if (const char* e = getenv("PCR_LOCAL_R1")) ctx->local_r1 = (float)atof(e);
-    if (const char* e = getenv("PCR_LOCAL_R2")) ctx->local_r2 = (float)atof(e);
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
     *out = ctx;

@@ -93,9 +93,8 @@ struct pcr_ctx {
     double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
     float r0_min = 0.0f;          // lower bound of the first cooperative search radius (cells)
     int warm_start = 0;           // per-point kernel: warm-start the search from the previous matches (measured: no gain)
-    int search_mode = 0;          // see LinParams::search_mode
     int min_blocks = 3;           // __launch_bounds__ min blocks/SM variant of the linearise kernels (2, 3 or 4)
-    float local_r1 = 1.0f, local_r2 = 3.0f;   // warm-start radii (cells) handled by the per-lane searches
+    float local_r1 = 1.0f;        // tile kernel: warm-start radius (cells) handled by the per-lane local search
     int lin_blocks_per_sm[4][5] = {};   // cached occupancy per (method, variant)
     pcr::DevBuf scan_x, scan_y, scan_z;
     pcr::DevBuf scan_prev;        // int[n_pad]: position matched by the previous linearisation (warm start)

@@ -33,10 +33,9 @@ struct LinParams {
     int use_lists;
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
-    float local_r1, local_r2; // mode 1: warm-start radius (cells) up to which the per-lane local search is used
+    float local_r1;           // tile kernel: warm-start radius (cells) up to which the per-lane local search is used
     float r0_min;             // lower bound of the first cooperative search radius (cells)
     int warm;                 // per-point kernel: use P.prev as warm start
-    int search_mode;          // 0: bound + packed pruned search (default); 1: local / cooperative (A/B)
     float r0_param;           // first search radius (grid units) when use_param_T; <= 0: take st->search_r0
     double T_param[16];
     int use_param_T;          // 1: transform comes from T_param, 0: from st->T (device loop)
@@ -210,24 +209,18 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_tile_kernel(const
             const float dw = ex * ex + ey * ey + ez * ez;
             if (dw < P.max_d2) d2 = dw; else pos = -1;
         }
-        const bool valid = px == px;
-        if (P.search_mode == 0) {
-            // mode 0: bound (warm start or cooperative first-hit search), then the packed pruned search
-            if (tile.any(valid && pos < 0)) tile_nn_search<G>(tile, P.grid, S, valid && pos < 0, qx, qy, qz, r0, P.max_d2, d2, pos, true);
-            warp_pruned_search<G>(tile, P.grid, valid && pos >= 0, qx, qy, qz, d2, pos);
-        } else {
-            // mode 1 (kept for A/B): per-lane local search for tight bounds, cooperative search otherwise
-            bool need = valid;
-            if (pos >= 0) {
-                const float r = sqrtf(d2) * P.grid.inv_h * 1.000001f + P.grid.slack;
-                if (r <= P.local_r1) {
-                    const float gx = (qx - P.grid.ox) * P.grid.inv_h, gy = (qy - P.grid.oy) * P.grid.inv_h, gz = (qz - P.grid.oz) * P.grid.inv_h;
-                    local_nn_search(P.grid, qx, qy, qz, gx, gy, gz, r, d2, pos);
-                    need = false;
-                }
+        // a tight warm-start bound (radius <= local_r1 cells) is settled by the per-lane local
+        // search; everything else (first iteration, large moves, outliers) searches cooperatively
+        bool need = px == px;
+        if (pos >= 0) {
+            const float r = sqrtf(d2) * P.grid.inv_h * 1.000001f + P.grid.slack;
+            if (r <= P.local_r1) {
+                const float gx = (qx - P.grid.ox) * P.grid.inv_h, gy = (qy - P.grid.oy) * P.grid.inv_h, gz = (qz - P.grid.oz) * P.grid.inv_h;
+                local_nn_search(P.grid, qx, qy, qz, gx, gy, gz, r, d2, pos);
+                need = false;
             }
-            if (tile.any(need)) tile_nn_search<G>(tile, P.grid, S, need, qx, qy, qz, r0, P.max_d2, d2, pos);
         }
+        if (tile.any(need)) tile_nn_search<G>(tile, P.grid, S, need, qx, qy, qz, r0, P.max_d2, d2, pos);
         P.prev[i] = pos;
         if (pos >= 0) {
             accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
@@ -301,12 +294,7 @@ __global__ void __launch_bounds__(kLinThreads) tile_nn_debug_kernel(const LinPar
         transform32(pose, px, py, pz, qx, qy, qz);
         float d2 = P.max_d2;
         int pos = -1;
-        if (P.search_mode == 0) {
-            tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos, true);
-            warp_pruned_search<G>(tile, P.grid, pos >= 0, qx, qy, qz, d2, pos);
-        } else {
-            tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
-        }
+        tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
         idx[i] = pos >= 0 ? (long long)__float_as_uint(P.grid.pts[pos].w) : -1ll;
         dist[i] = pos >= 0 ? sqrtf(d2) : __int_as_float(0x7f800000);
     }
@@ -529,8 +517,6 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.lists = ctx->vox_lists;
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
     P.local_r1 = ctx->local_r1;
-    P.local_r2 = ctx->local_r2;
-    P.search_mode = ctx->search_mode;
     P.warm = ctx->warm_start;
     P.r0_min = ctx->r0_min;
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();

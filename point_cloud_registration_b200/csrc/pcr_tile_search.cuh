@@ -95,14 +95,10 @@ __device__ __forceinline__ void local_nn_search(const GridView& Gv, float qx, fl
 // (max_dist^2, -1) or a WARM START: the squared distance to / position of any indexed point
 // (e.g. the previous iteration's match) -- an upper bound that lets the lane search the box
 // of that ball at once.  r0 = first search radius in grid units for lanes without a warm start.
-//
-// first_hit = true turns the search into a BOUND FINDER: a lane leaves as soon as it holds any
-// candidate (or is proven to have none within max_dist); warp_pruned_search then makes the
-// result exact.
 template <int G>
 __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& tile, const GridView& Gv, TileScratch<G>& S,
                                                bool valid, float qx, float qy, float qz, float r0, float max_d2,
-                                               float& best_d2, int& best_pos, bool first_hit = false) {
+                                               float& best_d2, int& best_pos) {
     constexpr int LISTCAP = 4 * G;
     const float gx = (qx - Gv.ox) * Gv.inv_h, gy = (qy - Gv.oy) * Gv.inv_h, gz = (qz - Gv.oz) * Gv.inv_h;
     bool pending = valid && (gx == gx) && (gy == gy) && (gz == gz) && Gv.n_pts != 0;
@@ -223,7 +219,7 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
             if (v2 < Gv.cnz - 1) { bound = fminf(bound, (float)(v2 + 1) - gz); open = true; }
             bound -= Gv.slack;
             const float rad = sqrtf(best_d2) * Gv.inv_h;
-            if (!open || rad <= bound || (first_hit && best_pos >= 0)) {
+            if (!open || rad <= bound) {
                 pending = false;
             } else if (best_pos >= 0) {
                 const float r = rad * 1.000001f + Gv.slack;          // box enclosing the ball, merged with the visited box
@@ -241,80 +237,6 @@ __device__ __forceinline__ void tile_nn_search(const cg::thread_block_tile<G>& t
                 lo2 = max(u2 - ez, 0); hi2 = min(v2 + ez, Gv.cnz - 1);
             }
         }
-    }
-}
-
-// Exact search for lanes that already hold an upper bound (best_d2, best_pos >= 0): the tile
-// walks the bricks of the union of the lanes' ball boxes TOGETHER (uniform loop, broadcast brick
-// loads); inside a brick every lane pops the occupied cells of ITS OWN ball box, prunes them by
-// box distance against ITS OWN bound and evaluates the survivors -- different lanes work on
-// different cells in the same instruction, so pruned per-query work is packed across the warp
-// instead of being serialised (per-lane search) or multiplied by 32 (shared candidate list).
-template <int G>
-__device__ __forceinline__ void warp_pruned_search(const cg::thread_block_tile<G>& tile, const GridView& Gv, bool active,
-                                                   float qx, float qy, float qz, float& best_d2, int& best_pos) {
-    const float gx = (qx - Gv.ox) * Gv.inv_h, gy = (qy - Gv.oy) * Gv.inv_h, gz = (qz - Gv.oz) * Gv.inv_h;
-    const float r = sqrtf(best_d2) * Gv.inv_h * 1.000001f + Gv.slack;
-    const int lo0 = cell_clamped(gx - r, Gv.cnx), hi0 = cell_clamped(gx + r, Gv.cnx);
-    const int lo1 = cell_clamped(gy - r, Gv.cny), hi1 = cell_clamped(gy + r, Gv.cny);
-    const int lo2 = cell_clamped(gz - r, Gv.cnz), hi2 = cell_clamped(gz + r, Gv.cnz);
-    const float h2 = Gv.h * Gv.h;
-    bool pending = active;
-    for (;;) {
-        const unsigned act = tile.ballot(pending);
-        if (act == 0u) break;
-        const int leader = __ffs(act) - 1;
-        const int L0 = tile.shfl(lo0, leader), H0 = tile.shfl(hi0, leader);
-        const int L1 = tile.shfl(lo1, leader), H1 = tile.shfl(hi1, leader);
-        const int L2 = tile.shfl(lo2, leader), H2 = tile.shfl(hi2, leader);
-        const int gap = max(max(max(L0 - hi0, lo0 - H0), max(L1 - hi1, lo1 - H1)), max(L2 - hi2, lo2 - H2));
-        const bool member = pending && gap <= 4;
-        const int bx0 = cg::reduce(tile, member ? lo0 : INT_MAX, cg::less<int>()) >> 2;
-        const int by0 = cg::reduce(tile, member ? lo1 : INT_MAX, cg::less<int>()) >> 2;
-        const int bz0 = cg::reduce(tile, member ? lo2 : INT_MAX, cg::less<int>()) >> 2;
-        const int bx1 = cg::reduce(tile, member ? hi0 : INT_MIN, cg::greater<int>()) >> 2;
-        const int by1 = cg::reduce(tile, member ? hi1 : INT_MIN, cg::greater<int>()) >> 2;
-        const int bz1 = cg::reduce(tile, member ? hi2 : INT_MIN, cg::greater<int>()) >> 2;
-        for (int bz = bz0; bz <= bz1; ++bz)
-            for (int by = by0; by <= by1; ++by)
-                for (int bx = bx0; bx <= bx1; ++bx) {
-                    const uint4 rec = __ldg(Gv.bricks + ((size_t)bz * Gv.bny + by) * Gv.bnx + bx);   // same address in every lane
-                    const unsigned long long occ = ((unsigned long long)rec.y << 32) | rec.x;
-                    if (occ == 0ull) continue;
-                    unsigned long long m = 0ull;
-                    if (member) {
-                        const int x0 = max(lo0 - bx * 4, 0), x1 = min(hi0 - bx * 4, 3);
-                        const int y0 = max(lo1 - by * 4, 0), y1 = min(hi1 - by * 4, 3);
-                        const int z0 = max(lo2 - bz * 4, 0), z1 = min(hi2 - bz * 4, 3);
-                        if (x0 <= x1 && y0 <= y1 && z0 <= z1) m = occ & brick_box_mask(x0, x1, y0, y1, z0, z1);
-                    }
-                    while (tile.any(m != 0ull)) {
-                        uint32_t s = 0u, len = 0u;
-                        if (m != 0ull) {
-                            const int bit = __ffsll((long long)m) - 1;
-                            m &= m - 1ull;
-                            const int cx = bx * 4 + (bit & 3), cy = by * 4 + ((bit >> 2) & 3), cz = bz * 4 + (bit >> 4);
-                            const float dx = fmaxf(fmaxf((float)cx - gx, gx - (float)(cx + 1)) - Gv.slack, 0.0f);
-                            const float dy = fmaxf(fmaxf((float)cy - gy, gy - (float)(cy + 1)) - Gv.slack, 0.0f);
-                            const float dz = fmaxf(fmaxf((float)cz - gz, gz - (float)(cz + 1)) - Gv.slack, 0.0f);
-                            if ((dx * dx + dy * dy + dz * dz) * h2 < best_d2) {
-                                const uint32_t ord = rec.z + (uint32_t)__popcll(occ & ((1ull << bit) - 1ull));
-                                s = __ldg(Gv.cell_start + ord);
-                                len = __ldg(Gv.cell_start + ord + 1) - s;
-                            }
-                        }
-                        const uint32_t maxlen = cg::reduce(tile, len, cg::greater<uint32_t>());
-                        for (uint32_t k = 0; k < maxlen; ++k) {
-                            if (k < len) {
-                                const float4 t = __ldg(Gv.pts + s + k);
-                                const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-                                const float d2 = ex * ex + ey * ey + ez * ez;
-                                if (d2 < best_d2) { best_d2 = d2; best_pos = (int)(s + k); }
-                            }
-                        }
-                    }
-                }
-        if (member) pending = false;
     }
 }
 

@@ -5,6 +5,8 @@
 the update, ``ValueError("Target is not set.")``, ``LinAlgError`` on a singular system) but runs
 the whole loop on the GPU (``pcr_align``) unless ``verbose=True`` or ``device_loop=False``, in
 which case the reference's host loop is replayed with one fused-kernel call per iteration."""
+import os
+
 import numpy as np
 
 from . import _lib
@@ -22,6 +24,7 @@ class Registration:
         self._dist = None          # (rank, world_size) once attach_communicator() was called
         self.scan_is_presharded = False   # multi-GPU: scans passed in are already this rank's tile
         self.sort_scan = True      # Morton-sort the scan on upload in align()
+        self.sort_scan_on_calc = os.environ.get("PCR_SORT_ON_CALC", "1") != "0"   # ... and in calc_H_g_e2(T, array)
         self.last_iterations = 0
         self.last_e2_trace = None
 
@@ -47,7 +50,7 @@ class Registration:
         if not self._is_target_set:
             raise ValueError("Target is not set.")
         if not isinstance(source, UploadedScan):
-            self._upload(source, sort=False)
+            self._upload(source, sort=self.sort_scan_on_calc)
         elif source.owner is not self:
             raise ValueError("scan handle belongs to another registration object")
         rec = self._ctx.linearize(self.method, np.asarray(cur_T, dtype=np.float64), self.max_dist)
