@@ -172,6 +172,12 @@ int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max
  * warp-cooperative search for sorted scans (kept for A/B measurements; slower on the measured
  * workloads, see profiles/).  Also settable at context creation through PCR_TILE_LANES. */
 int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes);
+/* Correspondence-search scheduling of the per-point search: mode 0 = every lane runs its query to
+ * completion (nested loops), mode 1 = persistent-lane "flat" search (a lane that finishes a query
+ * starts its next one at once; rounds of find-cell / evaluate <= ch candidates; cells are looked
+ * for once >= tau lanes of the warp are out of work).  Same exact result either way.  ch <= 0 /
+ * tau <= 0 keep the current values.  Also settable through PCR_SEARCH / PCR_FLAT_CH / PCR_FLAT_TAU. */
+int pcr_set_search_mode(pcr_ctx* ctx, int mode, int ch, int tau);
 /* Voxel-mean correspondences are read from exact per-cell candidate lists built with the voxels
  * (default on); 0 falls back to the general grid search everywhere (A/B and test hook). */
 int pcr_set_voxel_lists(pcr_ctx* ctx, int enable);
@@ -181,6 +187,10 @@ int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
  * points (which = 0) or the kept voxel means (which = 1); r0 = first search radius in cells.
  * idx = caller index of the match or -1, dist = Euclidean distance or inf. */
 int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_dist, double r0, int64_t* idx, float* dist);
+/* Test hook: correspondences parked by the LAST linearisation (any search variant): per resident
+ * scan point, in storage order (upload with sort <= 0 to keep the caller's order), the caller
+ * index of the matched target point (which = 0) / kept voxel (which = 1) or -1. */
+int pcr_debug_matches(pcr_ctx* ctx, int which, int64_t* idx);
 /* Grid statistics of the NN indices (cells, bricks, cell edge) for diagnostics. */
 int pcr_index_stats(pcr_ctx* ctx, int which /*0 target, 1 voxel*/, double* cell_edge, int64_t* n_cells,
                     int64_t* n_bricks, int64_t* n_points);

@@ -54,6 +54,8 @@ SYMBOLS = {
     "pcr_stream": (_i, [_vp, C.POINTER(_vp)]),
     "pcr_linearize_async": (_i, [_vp, _i, _vp, _d, _i]),
     "pcr_set_tile_lanes": (_i, [_vp, _i]),
+    "pcr_set_search_mode": (_i, [_vp, _i, _i, _i]),
+    "pcr_debug_matches": (_i, [_vp, _i, _vp]),
     "pcr_set_voxel_lists": (_i, [_vp, _i]),
     "pcr_voxel_list_stats": (_i, [_vp, _pi64, _pi64]),
     "pcr_debug_tile_nn": (_i, [_vp, _i, _vp, _d, _d, _vp, _vp]),
@@ -247,6 +249,16 @@ class Context:
 
     def set_tile_lanes(self, lanes):
         self._check(self._lib.pcr_set_tile_lanes(self._h, int(lanes)))
+
+    def set_search_mode(self, mode, ch=0, tau=0):
+        """mode 0: nested per-lane search, 1: persistent-lane flat search (see pcr_b200.h)."""
+        self._check(self._lib.pcr_set_search_mode(self._h, int(mode), int(ch), int(tau)))
+
+    def debug_matches(self, n_scan, which=0):
+        """Caller indices matched by the last linearisation, per resident scan point (storage order)."""
+        idx = np.empty(n_scan, dtype=np.int64)
+        self._check(self._lib.pcr_debug_matches(self._h, int(which), _ptr(idx)))
+        return idx
 
     def debug_tile_nn(self, n_scan, T, max_dist, r0=0.5, which=0):
         T = np.ascontiguousarray(T, dtype=np.float64)

@@ -883,6 +883,9 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_R0_MIN")) ctx->r0_min = (float)atof(e);
     if (const char* e = getenv("PCR_WARM")) ctx->warm_start = atoi(e);
     if (const char* e = getenv("PCR_LOCAL_R1")) ctx->local_r1 = (float)atof(e);
+    if (const char* e = getenv("PCR_SEARCH")) ctx->search_mode = (!strcmp(e, "flat") || atoi(e) == 1) ? 1 : 0;
+    if (const char* e = getenv("PCR_FLAT_CH")) ctx->flat_ch = atoi(e) >= 4 ? atoi(e) : 32;
+    if (const char* e = getenv("PCR_FLAT_TAU")) ctx->flat_tau = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : 1;
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
     *out = ctx;

@@ -95,7 +95,10 @@ struct pcr_ctx {
     int warm_start = 0;           // per-point kernel: warm-start the search from the previous matches (measured: no gain)
     int min_blocks = 3;           // __launch_bounds__ min blocks/SM variant of the linearise kernels (2, 3 or 4)
     float local_r1 = 1.0f;        // tile kernel: warm-start radius (cells) handled by the per-lane local search
-    int lin_blocks_per_sm[4][5] = {};   // cached occupancy per (method, variant)
+    int search_mode = 0;          // 0: nested per-lane search (variant B), 1: persistent-lane flat search (variant C)
+    int flat_ch = 32;             // flat search: candidates per lane and round
+    int flat_tau = 1;             // flat search: lanes out of work before phase A runs
+    int lin_blocks_per_sm[4][8] = {};   // cached occupancy per (method, variant)
     pcr::DevBuf scan_x, scan_y, scan_z;
     pcr::DevBuf scan_prev;        // int[n_pad]: position matched by the previous linearisation (warm start)
     int prev_which = -1;          // index the positions refer to (0 target grid, 1 voxel grid, -1 none)

@@ -17,6 +17,7 @@
 
 #include "pcr_context.cuh"
 #include "pcr_grid.cuh"
+#include "pcr_flat_search.cuh"
 #include "pcr_linalg.cuh"
 #include "pcr_terms.cuh"
 #include "pcr_tile_search.cuh"
@@ -36,6 +37,9 @@ struct LinParams {
     float local_r1;           // tile kernel: warm-start radius (cells) up to which the per-lane local search is used
     float r0_min;             // lower bound of the first cooperative search radius (cells)
     int warm;                 // per-point kernel: use P.prev as warm start
+    int flat_ch;              // flat kernel: candidates evaluated per lane and round
+    int flat_tau;             // flat kernel: lanes that must be out of work before the warp looks for new cells
+    uint32_t list_last;       // last valid offset of lists.list_idx
     float r0_param;           // first search radius (grid units) when use_param_T; <= 0: take st->search_r0
     double T_param[16];
     int use_param_T;          // 1: transform comes from T_param, 0: from st->T (device loop)
@@ -276,6 +280,79 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_lane_kernel(const
     reduce_and_finish<METHOD>(P, sh, acc);
 }
 
+
+// ---- variant C: persistent-lane ("flat") search ---------------------------------------------------
+// Pass 1 is ONE warp loop of rounds { phase A: lanes without candidates find their next cell,
+// plan their next pass, or -- when their query is finished -- park the result and start their
+// next query | phase B: every lane evaluates <= flat_ch candidates }.  A lane never waits for the
+// slowest query of its row (the nested search's loss, 10-13 active lanes per instruction), and
+// phase A only runs once >= flat_tau lanes are out of work, so it executes with many lanes
+// active.  Lane t still owns scan slots t, t + stride, ... : pass 2 (identical to variant B) reads
+// back exactly what the same thread parked, and the summation order stays fixed.
+template <int METHOD, int MINB>
+__global__ void __launch_bounds__(kLinThreads, MINB) linearize_flat_kernel(const LinParams P) {
+    constexpr int NACC = NAcc<METHOD>::value;
+    constexpr bool kLists = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
+    __shared__ BlockShared sh;
+    Pose32 pose;
+    float r0;
+    if (!load_pose(P, sh, pose, r0)) return;
+    const long long stride = (long long)gridDim.x * kLinThreads;
+    const long long first = blockIdx.x * (long long)kLinThreads + threadIdx.x;
+    {
+        FlatLane L;
+        L.p = L.e = 0u;
+        long long i = first;
+        bool active = false, lmode = false;
+        bool done = i >= P.n_pad;
+        const bool use_lists = kLists && P.use_lists;
+        const int ch = P.flat_ch, tau = P.flat_tau;
+        for (;;) {
+            const bool need = !done && L.p == L.e;
+            const unsigned needm = __ballot_sync(0xffffffffu, need);
+            const unsigned havem = __ballot_sync(0xffffffffu, !done && L.p != L.e);
+            if ((needm | havem) == 0u) break;
+            if (need && (__popc(needm) >= tau || havem == 0u)) {
+                while (L.p == L.e) {
+                    if (active) {
+                        if (!lmode) {
+                            if (flat_next_cell(P.grid, L)) break;
+                            if (flat_next_pass(P.grid, L)) continue;
+                        }
+                        P.prev[i] = L.best_pos;
+                        i += stride;
+                        active = false;
+                    }
+                    if (i >= P.n_pad) { done = true; break; }
+                    const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+                    float qx, qy, qz;
+                    transform32(pose, px, py, pz, qx, qy, qz);
+                    if (use_lists && flat_begin_list(P.grid, P.lists, L, qx, qy, qz, P.max_d2)) { lmode = true; active = true; }
+                    else if (flat_begin(P.grid, L, qx, qy, qz, P.max_d2)) { lmode = false; active = true; }
+                    else { P.prev[i] = -1; i += stride; }
+                }
+            }
+            flat_eval(P.grid, L, ch, (kLists && lmode) ? P.lists.list_idx : nullptr, P.list_last);
+        }
+    }
+
+    float acc[NACC + 1];
+#pragma unroll
+    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
+    for (long long i = first; i < P.n_pad; i += stride) {
+        const int pos = P.prev[i];                       // written by this very thread in pass 1
+        if (pos < 0) continue;
+        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+        float qx, qy, qz;
+        transform32(pose, px, py, pz, qx, qy, qz);
+        accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
+        const float4 t = __ldg(P.grid.pts + pos);
+        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+        acc[NACC] += sqrtf(ex * ex + ey * ey + ez * ez);
+    }
+    reduce_and_finish<METHOD>(P, sh, acc);
+}
+
 // Debug / test kernel: tile-cooperative NN of the resident scan under T_param -> per scan slot
 // (storage order) the matched position's payload index and the distance.
 template <int G>
@@ -298,6 +375,13 @@ __global__ void __launch_bounds__(kLinThreads) tile_nn_debug_kernel(const LinPar
         idx[i] = pos >= 0 ? (long long)__float_as_uint(P.grid.pts[pos].w) : -1ll;
         dist[i] = pos >= 0 ? sqrtf(d2) : __int_as_float(0x7f800000);
     }
+}
+
+__global__ void matches_kernel(const int* __restrict__ prev, const float4* __restrict__ pts, long long n, long long* __restrict__ idx) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int pos = prev[i];
+    idx[i] = pos >= 0 ? (long long)__float_as_uint(pts[pos].w) : -1ll;
 }
 
 // Gauss-Newton step as its own tiny kernel (multi-GPU path: runs after the all-reduce).
@@ -518,6 +602,9 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
     P.local_r1 = ctx->local_r1;
     P.warm = ctx->warm_start;
+    P.flat_ch = ctx->flat_ch;
+    P.flat_tau = ctx->flat_tau;
+    P.list_last = ctx->n_list_entries > 0 ? (uint32_t)(ctx->n_list_entries - 1) : 0u;
     P.r0_min = ctx->r0_min;
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
     const float md = (float)max_dist;
@@ -534,7 +621,8 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     //  so their costs add up instead of overlapping -- profiles/r1_notes.md)
     const bool tile = ctx->scan_sorted && ctx->tile_lanes == 32;
     const int mb = ctx->min_blocks;                       // 2, 3 or 4 resident blocks per SM requested
-    const int v = tile ? (mb >= 3 ? 1 : 0) : (mb >= 4 ? 4 : (mb == 3 ? 3 : 2));
+    const bool flat = !tile && ctx->search_mode == 1;
+    const int v = flat ? (mb >= 4 ? 7 : (mb == 3 ? 6 : 5)) : tile ? (mb >= 3 ? 1 : 0) : (mb >= 4 ? 4 : (mb == 3 ? 3 : 2));
     int& per_sm = ctx->lin_blocks_per_sm[METHOD][v];
     if (per_sm == 0) {
         switch (v) {
@@ -542,7 +630,10 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
             case 1: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 32, 3>); break;
             case 2: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 2>); break;
             case 3: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 3>); break;
-            default: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 4>); break;
+            case 4: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 4>); break;
+            case 5: per_sm = blocks_per_sm(linearize_flat_kernel<METHOD, 2>); break;
+            case 6: per_sm = blocks_per_sm(linearize_flat_kernel<METHOD, 3>); break;
+            default: per_sm = blocks_per_sm(linearize_flat_kernel<METHOD, 4>); break;
         }
     }
     const int blocks = lin_grid_blocks(ctx, P.n_pad, per_sm);
@@ -551,7 +642,10 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
         case 1: linearize_tile_kernel<METHOD, 32, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
         case 2: linearize_lane_kernel<METHOD, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
         case 3: linearize_lane_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        default: linearize_lane_kernel<METHOD, 4><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 4: linearize_lane_kernel<METHOD, 4><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 5: linearize_flat_kernel<METHOD, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        case 6: linearize_flat_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+        default: linearize_flat_kernel<METHOD, 4><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
     }
     PCR_LAUNCH_CHECK();
     return PCR_OK;
@@ -798,10 +892,38 @@ int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_di
     return PCR_OK;
 }
 
+int pcr_debug_matches(pcr_ctx* ctx, int which, int64_t* idx) {
+    if (!ctx || !idx) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    const Grid& g = which == 0 ? ctx->tgt_grid : ctx->vox_grid;
+    if (!g.built) return fail(ctx, PCR_ERR_STATE, "pcr_debug_matches: index not built");
+    if (!ctx->scan_set || ctx->n_scan == 0) return fail(ctx, PCR_ERR_STATE, "pcr_debug_matches: scan not set");
+    if (ctx->prev_which != which) return fail(ctx, PCR_ERR_STATE, "pcr_debug_matches: no linearisation against this index yet");
+    DevBuf di;
+    PCR_CUDA(di.ensure((size_t)ctx->n_scan * 8));
+    matches_kernel<<<(unsigned)((ctx->n_scan + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_prev.as<int>(), g.view.pts, ctx->n_scan, di.as<long long>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaMemcpyAsync(idx, di.p, (size_t)ctx->n_scan * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    di.release();
+    return PCR_OK;
+}
+
 int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes) {
     if (!ctx) return PCR_ERR_ARG;
     if (lanes != 0 && lanes != 32) return fail(ctx, PCR_ERR_ARG, "pcr_set_tile_lanes: lanes must be 0 (per-point search) or 32 (warp-cooperative search)");
     ctx->tile_lanes = lanes;
+    return PCR_OK;
+}
+
+int pcr_set_search_mode(pcr_ctx* ctx, int mode, int ch, int tau) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (mode != 0 && mode != 1) return fail(ctx, PCR_ERR_ARG, "pcr_set_search_mode: mode must be 0 (nested) or 1 (flat)");
+    if (ch > 0 && ch < 4) return fail(ctx, PCR_ERR_ARG, "pcr_set_search_mode: ch must be >= 4");
+    if (tau > 32) return fail(ctx, PCR_ERR_ARG, "pcr_set_search_mode: tau must be <= 32");
+    ctx->search_mode = mode;
+    if (ch > 0) ctx->flat_ch = ch;
+    if (tau > 0) ctx->flat_tau = tau;
     return PCR_OK;
 }
 
