@@ -160,12 +160,21 @@ def run_reference(args, wl_name, wl, world, rank):
     bounded = n_total > 2_000_000
     n_t = 10_000_000 if (bounded and wl["cls"] == "PlaneICP") else n_total
     n_t = min(n_t, n_total)
-    n_s = 1_000_000 if bounded else n_total
-    log(f"reference arm: {wl['cls']} target {n_t} pts, scan sample {n_s} pts, {cores} host threads")
-    target, scan = host_data(wl, n_t, sample=n_s if n_s < n_t else None)
+    target, scan_all = host_data(wl, n_t)
     t0 = time.perf_counter()
     o = oracle_object(wl, target)
     setup_s = time.perf_counter() - t0
+    # bounded sample: calibrate the per-point cost on 50k scan points, then size the sample so that
+    # the whole --steps K --warmup W run stays near REF_BUDGET_S seconds of CPU work
+    rng = np.random.default_rng(0)
+    cal = scan_all[rng.choice(len(scan_all), size=min(50_000, len(scan_all)), replace=False)].astype(np.float32)
+    time_oracle_steps(o, cal, [np.eye(4)], 1, 1)
+    per_point = time_oracle_steps(o, cal, [np.eye(4)], 2, 0) / len(cal)
+    budget_s = float(os.environ.get("REF_BUDGET_S", "100"))
+    n_s = int(budget_s / (per_point * (args.steps + args.warmup)))
+    n_s = max(20_000, min(n_s, 1_000_000 if bounded else n_total, len(scan_all)))
+    log(f"reference arm: {wl['cls']} target {n_t} pts, scan sample {n_s} pts ({per_point * 1e9:.0f} ns/pt calibrated), {cores} host threads")
+    scan = scan_all if n_s == len(scan_all) else scan_all[np.sort(rng.choice(len(scan_all), size=n_s, replace=False))]
     trace = []
     o.max_iter = 30 if not bounded else 4
     o.align(scan, np.eye(4), trace=trace)
@@ -174,7 +183,7 @@ def run_reference(args, wl_name, wl, world, rank):
     scale = n_total / n_s                      # a full step costs ~ (n_total / n_s) sampled steps
     value = 1.0 / (sec * scale)
     sample = (f"{n_s}-pt scan sample vs {n_t}-pt target, time scaled x{scale:.1f} to the {n_total}-pt workload"
-              if bounded else f"full {n_total}-pt workload")
+              if n_s < n_total else f"full {n_total}-pt workload")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": sec * scale * 1e3, "higher_is_better": True,

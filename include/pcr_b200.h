@@ -182,6 +182,11 @@ int pcr_set_search_mode(pcr_ctx* ctx, int mode, int ch, int tau);
  * (default on); 0 falls back to the general grid search everywhere (A/B and test hook). */
 int pcr_set_voxel_lists(pcr_ctx* ctx, int enable);
 int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
+/* Target-point correspondences (ICP / PlaneICP) enumerate their candidate cells through per-cell
+ * neighbour lists built with the NN index (default on); 0 walks the brick grid instead (A/B and
+ * test hook).  Same exact nearest neighbour either way. */
+int pcr_set_nbr_lists(pcr_ctx* ctx, int enable);
+int pcr_nbr_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
 /* Test hook: exact NN of every resident scan point (storage order; upload with sort <= 0 to keep
  * the caller's order) under transform T through the TILE-COOPERATIVE search, against the target
  * points (which = 0) or the kept voxel means (which = 1); r0 = first search radius in cells.

@@ -123,6 +123,16 @@ __global__ void gather_points_kernel(const float* __restrict__ xyz, const uint32
     pts[i] = make_float4(xyz[3 * (size_t)j], xyz[3 * (size_t)j + 1], xyz[3 * (size_t)j + 2], __uint_as_float(j));
 }
 
+// Four sentinel records behind the last indexed point (and four list entries pointing at the
+// first of them): candidate loops read in groups of four without clamping; a sentinel is
+// infinitely far from every query and can never win.
+__global__ void pad_tail_kernel(float4* __restrict__ pts, long long n, uint32_t* __restrict__ list_idx, long long n_entries) {
+    if (threadIdx.x < 4) {
+        if (pts) pts[n + threadIdx.x] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, __uint_as_float(0xffffffffu));
+        if (list_idx) list_idx[n_entries + threadIdx.x] = (uint32_t)n;
+    }
+}
+
 static inline int blocks_for(long long n, int threads) { return (int)((n + threads - 1) / threads); }
 
 static int bits_for(unsigned long long v) {   // number of bits needed to represent values < v
@@ -246,7 +256,9 @@ int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, Dev
         PCR_CUDA(g.bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
         PCR_CUDA(cudaMemsetAsync(g.bricks.p, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
         PCR_CUDA(g.cell_start.ensure(((size_t)n_cells + 1) * 4));
-        PCR_CUDA(g.pts.ensure((size_t)n * sizeof(float4)));
+        PCR_CUDA(g.pts.ensure(((size_t)n + 4) * sizeof(float4)));
+        pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(g.pts.as<float4>(), n, nullptr, 0);
+        PCR_LAUNCH_CHECK();
         grid_fill_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(k_out, flags, ords, n, n_cells,
                                                                       g.bricks.as<BrickRec>(), g.cell_start.as<uint32_t>());
         PCR_LAUNCH_CHECK();
@@ -596,14 +608,14 @@ constexpr int kBandDilate = 2;     // cells within this Chebyshev distance of a 
 constexpr int kListRadius = 3;     // list build looks at the (2R+1)^3 neighbourhood; exact while D_C < R
 
 // mark the neighbourhood of every kept voxel as "band" (cells that get a list)
-__global__ void band_mark_kernel(GridView G, BrickRec* __restrict__ lbricks) {
+__global__ void band_mark_kernel(GridView G, BrickRec* __restrict__ lbricks, int dilate) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= G.n_pts) return;
     const float4 m = G.pts[v];
     const int cx = cell_of((m.x - G.ox) * G.inv_h, G.cnx), cy = cell_of((m.y - G.oy) * G.inv_h, G.cny), cz = cell_of((m.z - G.oz) * G.inv_h, G.cnz);
-    const int x0 = max(cx - kBandDilate, 0), x1 = min(cx + kBandDilate, G.cnx - 1);
-    const int y0 = max(cy - kBandDilate, 0), y1 = min(cy + kBandDilate, G.cny - 1);
-    const int z0 = max(cz - kBandDilate, 0), z1 = min(cz + kBandDilate, G.cnz - 1);
+    const int x0 = max(cx - dilate, 0), x1 = min(cx + dilate, G.cnx - 1);
+    const int y0 = max(cy - dilate, 0), y1 = min(cy + dilate, G.cny - 1);
+    const int z0 = max(cz - dilate, 0), z1 = min(cz + dilate, G.cnz - 1);
     for (int bz = z0 >> 2; bz <= z1 >> 2; ++bz)
         for (int by = y0 >> 2; by <= y1 >> 2; ++by)
             for (int bx = x0 >> 2; bx <= x1 >> 2; ++bx) {
@@ -707,7 +719,7 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     PCR_CUDA(ctx->vox_lbricks.ensure((size_t)nbricks * sizeof(BrickRec)));
     PCR_CUDA(cudaMemsetAsync(ctx->vox_lbricks.p, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
     BrickRec* lb = ctx->vox_lbricks.as<BrickRec>();
-    band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb);
+    band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb, kBandDilate);
     PCR_LAUNCH_CHECK();
     PCR_CUDA(ctx->tmp_a.ensure((size_t)(nbricks + 1) * 4 * 2));
     uint32_t* bcnt = ctx->tmp_a.as<uint32_t>();
@@ -736,7 +748,9 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     uint32_t n_entries = 0;
     PCR_CUDA(cudaMemcpyAsync(&n_entries, ctx->vox_list_start.as<uint32_t>() + n_band, 4, cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-    PCR_CUDA(ctx->vox_list_idx.ensure(((size_t)n_entries + 1) * 4));
+    PCR_CUDA(ctx->vox_list_idx.ensure(((size_t)n_entries + 4) * 4));
+    pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(nullptr, (long long)G.n_pts, ctx->vox_list_idx.as<uint32_t>(), (long long)n_entries);
+    PCR_LAUNCH_CHECK();
     list_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, nullptr, ctx->vox_list_start.as<uint32_t>(),
                                                                                ctx->vox_list_idx.as<uint32_t>());
     PCR_LAUNCH_CHECK();
@@ -746,6 +760,117 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     ctx->vox_lists.list_idx = ctx->vox_list_idx.as<uint32_t>();
     ctx->n_band_cells = n_band;
     ctx->n_list_entries = n_entries;
+    return PCR_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// per-cell neighbour lists over the target-point grid (see NbrLists in pcr_common.cuh)
+// ---------------------------------------------------------------------------------------
+// visiting order of the 3x3x3 block: own cell, 6 face, 12 edge, 8 corner neighbours
+__constant__ signed char kNbrOrder[27][3] = {
+    {0, 0, 0},
+    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+    {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}, {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1},
+    {-1, -1, -1}, {1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}, {1, 1, 1}};
+
+// One thread per (brick, bit) of the band.  FILL = false: counts[ordinal] = number of occupied
+// cells in the 3x3x3 block; FILL = true: write the entries (own cell first -- nbr_nn relies on it).
+template <bool FILL>
+__global__ void nbr_build_kernel(GridView G, const BrickRec* __restrict__ nbricks_rec, unsigned long long nbricks,
+                                 uint32_t* __restrict__ counts, const uint32_t* __restrict__ nstart, uint2* __restrict__ entries,
+                                 int* __restrict__ overflow) {
+    const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    const unsigned long long b = tid >> 6;
+    const int bit = (int)(tid & 63ull);
+    if (b >= nbricks) return;
+    const BrickRec lr = nbricks_rec[b];
+    if (!((lr.mask >> bit) & 1ull)) return;
+    const uint32_t ord = lr.base + (uint32_t)__popcll(lr.mask & ((1ull << bit) - 1ull));
+    const int bx = (int)(b % (unsigned long long)G.bnx), by = (int)((b / (unsigned long long)G.bnx) % (unsigned long long)G.bny),
+              bz = (int)(b / ((unsigned long long)G.bnx * G.bny));
+    const int cx = bx * 4 + (bit & 3), cy = by * 4 + ((bit >> 2) & 3), cz = bz * 4 + (bit >> 4);
+    uint32_t n_out = 0, w = FILL ? nstart[ord] : 0u;
+    long long cached = -1;
+    uint4 rec = make_uint4(0, 0, 0, 0);
+    for (int o = 0; o < 27; ++o) {
+        const int dx = kNbrOrder[o][0], dy = kNbrOrder[o][1], dz = kNbrOrder[o][2];
+        const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+        if (nx < 0 || ny < 0 || nz < 0 || nx >= G.cnx || ny >= G.cny || nz >= G.cnz) continue;
+        const long long nbk = ((long long)(nz >> 2) * G.bny + (ny >> 2)) * G.bnx + (nx >> 2);
+        if (nbk != cached) { rec = G.bricks[nbk]; cached = nbk; }
+        const unsigned long long occ = ((unsigned long long)rec.y << 32) | rec.x;
+        const int nbit = brick_bit(nx, ny, nz);
+        if (!((occ >> nbit) & 1ull)) continue;
+        if (!FILL && o == 0) {                                // every occupied cell is some band cell's own cell
+            const uint32_t o2 = rec.z + (uint32_t)__popcll(occ & ((1ull << nbit) - 1ull));
+            if (G.cell_start[o2 + 1] - G.cell_start[o2] >= (1u << 26)) atomicOr(overflow, 1);   // entry format holds 26-bit counts
+        }
+        if (FILL) {
+            const uint32_t o2 = rec.z + (uint32_t)__popcll(occ & ((1ull << nbit) - 1ull));
+            const uint32_t s = G.cell_start[o2], e = G.cell_start[o2 + 1];
+            const uint32_t code = (uint32_t)((dx + 1) | ((dy + 1) << 2) | ((dz + 1) << 4));
+            entries[w++] = make_uint2(s, (code << 26) | (e - s));
+        }
+        ++n_out;
+    }
+    if (!FILL) counts[ord] = n_out;
+}
+
+static int build_nbr_lists(pcr_ctx* ctx) {
+    Grid& g = ctx->tgt_grid;
+    ctx->tgt_nbr = NbrLists{};
+    ctx->n_nbr_band = ctx->n_nbr_entries = 0;
+    if (!g.built || g.view.n_pts == 0) return PCR_OK;
+    if (const char* e = getenv("PCR_NBR_LISTS")) if (atoi(e) == 0) return PCR_OK;
+    const GridView& G = g.view;
+    const unsigned long long nbricks = (unsigned long long)G.bnx * G.bny * G.bnz;
+    PCR_CUDA(ctx->nbr_bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
+    PCR_CUDA(cudaMemsetAsync(ctx->nbr_bricks.p, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
+    BrickRec* lb = ctx->nbr_bricks.as<BrickRec>();
+    band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb, 1);
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(ctx->tmp_a.ensure((size_t)(nbricks + 1) * 4 * 2));
+    uint32_t* bcnt = ctx->tmp_a.as<uint32_t>();
+    uint32_t* bbase = bcnt + (nbricks + 1);
+    PCR_CUDA(cudaMemsetAsync(bcnt, 0, (size_t)(nbricks + 1) * 4, ctx->stream));
+    brick_popc_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bcnt);
+    PCR_LAUNCH_CHECK();
+    int rc = exclusive_sum_u32(ctx, bcnt, bbase, (long long)nbricks + 1);
+    if (rc) return rc;
+    uint32_t n_band = 0;
+    PCR_CUDA(cudaMemcpyAsync(&n_band, bbase + nbricks, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    brick_base_set_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bbase);
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(ctx->tmp_b.ensure(((size_t)n_band + 1) * 4));
+    PCR_CUDA(ctx->nbr_start.ensure(((size_t)n_band + 1) * 4));
+    uint32_t* counts = ctx->tmp_b.as<uint32_t>();
+    PCR_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_band + 1) * 4, ctx->stream));
+    const long long nthreads = (long long)nbricks * 64;
+    PCR_CUDA(ctx->tmp_e.ensure(64));
+    int* d_overflow = ctx->tmp_e.as<int>();
+    PCR_CUDA(cudaMemsetAsync(d_overflow, 0, 4, ctx->stream));
+    nbr_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, counts, nullptr, nullptr, d_overflow);
+    PCR_LAUNCH_CHECK();
+    rc = exclusive_sum_u32(ctx, counts, ctx->nbr_start.as<uint32_t>(), (long long)n_band + 1);
+    if (rc) return rc;
+    uint32_t n_entries = 0;
+    int overflow = 0;
+    PCR_CUDA(cudaMemcpyAsync(&n_entries, ctx->nbr_start.as<uint32_t>() + n_band, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (overflow) return PCR_OK;                              // a cell with >= 2^26 points: keep the general search
+    PCR_CUDA(ctx->nbr_entries.ensure(((size_t)n_entries + 1) * sizeof(uint2)));
+    nbr_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, nullptr, ctx->nbr_start.as<uint32_t>(),
+                                                                              ctx->nbr_entries.as<uint2>(), nullptr);
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->tgt_nbr.bricks = ctx->nbr_bricks.as<uint4>();
+    ctx->tgt_nbr.nstart = ctx->nbr_start.as<uint32_t>();
+    ctx->tgt_nbr.entries = ctx->nbr_entries.as<uint2>();
+    ctx->n_nbr_band = n_band;
+    ctx->n_nbr_entries = n_entries;
     return PCR_OK;
 }
 
@@ -778,7 +903,9 @@ static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     const unsigned long long nbricks = (unsigned long long)F.bn[0] * F.bn[1] * F.bn[2];
     PCR_CUDA(g.bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
     PCR_CUDA(g.cell_start.ensure((nk + 1) * 4));
-    PCR_CUDA(g.pts.ensure(nk * sizeof(float4)));
+    PCR_CUDA(g.pts.ensure((nk + 4) * sizeof(float4)));
+    pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(g.pts.as<float4>(), (long long)n_keep, nullptr, 0);
+    PCR_LAUNCH_CHECK();
     brick_base_init_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(g.bricks.as<BrickRec>(), nbricks);
     PCR_LAUNCH_CHECK();
     voxel_finalize_kernel<<<blocks_for(F.n_seg, 128), 128, 0, ctx->stream>>>(
@@ -901,6 +1028,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->vox_mean.release(); ctx->vox_cov.release(); ctx->vox_norm.release(); ctx->vox_icov.release(); ctx->vox_count.release();
     ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
     ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release();
+    ctx->nbr_bricks.release(); ctx->nbr_start.release(); ctx->nbr_entries.release();
     ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();
     ctx->partials.release(); ctx->state.release();
     ctx->tmp_a.release(); ctx->tmp_b.release(); ctx->tmp_c.release(); ctx->tmp_d.release(); ctx->tmp_e.release(); ctx->cub_tmp.release();
@@ -918,6 +1046,8 @@ int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n) {
     if (!xyz || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_set_target_points: empty target");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->tgt_grid.release();
+    ctx->tgt_nbr = NbrLists{};                  // lists refer to the released grid
+    ctx->n_nbr_band = ctx->n_nbr_entries = 0;
     ctx->has_normals = false;
     PCR_CUDA(ctx->tgt_xyz.ensure((size_t)n * 12));
     PCR_CUDA(cudaMemcpyAsync(ctx->tgt_xyz.p, xyz, (size_t)n * 12,
@@ -932,7 +1062,9 @@ int pcr_build_nn_index(pcr_ctx* ctx) {
     if (ctx->n_tgt <= 0) return fail(ctx, PCR_ERR_STATE, "pcr_build_nn_index: target points not set");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->tgt_grid_epoch++;
-    return build_point_grid(ctx, ctx->tgt_xyz.as<float>(), ctx->n_tgt, ctx->tgt_grid, nullptr);
+    int rc = build_point_grid(ctx, ctx->tgt_xyz.as<float>(), ctx->n_tgt, ctx->tgt_grid, nullptr);
+    if (rc) return rc;
+    return build_nbr_lists(ctx);
 }
 
 int pcr_estimate_normals(pcr_ctx* ctx, int k) {
@@ -1096,6 +1228,19 @@ int pcr_index_stats(pcr_ctx* ctx, int which, double* cell_edge, int64_t* n_cells
 int pcr_set_voxel_lists(pcr_ctx* ctx, int enable) {
     if (!ctx) return PCR_ERR_ARG;
     ctx->use_voxel_lists = enable ? 1 : 0;
+    return PCR_OK;
+}
+
+int pcr_set_nbr_lists(pcr_ctx* ctx, int enable) {
+    if (!ctx) return PCR_ERR_ARG;
+    ctx->use_nbr_lists = enable ? 1 : 0;
+    return PCR_OK;
+}
+
+int pcr_nbr_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (band_cells) *band_cells = ctx->n_nbr_band;
+    if (entries) *entries = ctx->n_nbr_entries;
     return PCR_OK;
 }
 

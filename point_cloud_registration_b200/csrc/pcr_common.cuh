@@ -148,6 +148,21 @@ struct CandLists {
     const uint32_t* list_idx;    // positions in GridView::pts
 };
 
+// Per-cell neighbour lists over the target-point grid: for every "band" cell C (a cell within
+// Chebyshev distance 1 of an occupied cell) the occupied cells of the 3x3x3 block around C, own
+// cell first, then face, edge and corner neighbours.  One entry = the neighbour's point range in
+// GridView::pts plus its offset from C:
+//     entries[k].x = first point,  entries[k].y = (code << 26) | count,
+//     code = (dx + 1) | (dy + 1) << 2 | (dz + 1) << 4
+// A query enumerates its candidate cells by reading this short list instead of walking brick
+// records and occupancy masks (the walk was ~2/3 of the search's instructions); if the ball of its
+// best match leaves the 3x3x3 block, or its cell has no list, the general search takes over.
+struct NbrLists {
+    const uint4* bricks;         // (band mask lo, hi, ordinal of first band cell, unused), brick layout of the grid
+    const uint32_t* nstart;      // [n_band + 1]
+    const uint2* entries;
+};
+
 PCR_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
 PCR_HD int cell_of(float g, int n) {          // grid coordinate -> clamped cell index
@@ -161,11 +176,14 @@ PCR_HD int brick_bit(int cx, int cy, int cz) { return ((cz & 3) << 4) | ((cy & 3
 // 64-bit mask of the cells of one brick whose local coordinates lie in [x0,x1]x[y0,y1]x[z0,z1]
 // (all in 0..3, inclusive, lo <= hi).
 PCR_HD unsigned long long brick_box_mask(int x0, int x1, int y0, int y1, int z0, int z1) {
-    unsigned long long mx = ((2ull << x1) - (1ull << x0)) * 0x1111111111111111ull;            // x nibble pattern
-    unsigned long long my = ((2ull << (4 * y1 + 3)) - (1ull << (4 * y0))) * 0x0001000100010001ull;  // y rows in every z slab
-    unsigned long long hi = (z1 == 3) ? ~0ull : ((1ull << (16 * (z1 + 1))) - 1ull);
-    unsigned long long mz = hi & ~((1ull << (16 * z0)) - 1ull);
-    return mx & my & mz;
+    // 32-bit arithmetic only (64-bit multiplies are slow on the GPU): one z slab is 16 bits
+    const uint32_t ax = (2u << x1) - (1u << x0);                      // x pattern of one row (4 bits)
+    const uint32_t ay = (2u << (4 * y1 + 3)) - (1u << (4 * y0));      // rows y0..y1 of one slab (16 bits)
+    const uint32_t slab = (ax * 0x1111u) & ay;
+    const uint32_t two = slab | (slab << 16);                         // the same pattern in two slabs
+    const uint32_t lo = (z0 <= 0 ? 0x0000ffffu : 0u) | ((z0 <= 1 && z1 >= 1) ? 0xffff0000u : 0u);   // slabs 0, 1
+    const uint32_t hi = ((z0 <= 2 && z1 >= 2) ? 0x0000ffffu : 0u) | (z1 >= 3 ? 0xffff0000u : 0u);   // slabs 2, 3
+    return ((unsigned long long)(two & hi) << 32) | (unsigned long long)(two & lo);
 }
 
 }  // namespace pcr

@@ -69,6 +69,10 @@ struct pcr_ctx {
     pcr::DevBuf tgt_nrm_sorted;   // float4[n], same order as tgt_grid.pts
     pcr::DevBuf tgt_nrm_orig;     // float[3n], caller order
     bool has_normals = false;
+    pcr::DevBuf nbr_bricks, nbr_start, nbr_entries;   // per-cell neighbour lists over the target grid
+    pcr::NbrLists tgt_nbr{};      // null pointers = not built
+    long long n_nbr_band = 0, n_nbr_entries = 0;
+    int use_nbr_lists = 1;
 
     // ---- voxel statistics (VPlaneICP / NDT / VoxelGrid facade) ----
     long long n_vox = 0;          // kept voxels

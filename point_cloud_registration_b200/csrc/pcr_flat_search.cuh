@@ -162,15 +162,14 @@ PCR_HD bool flat_find_work(const GridView& G, FlatLane& L) {
 
 // Phase B: evaluate up to `ch` candidates of the current range, four at a time.  `list_idx` null:
 // the range [p, e) addresses G.pts directly (a cell); otherwise it addresses list_idx (a per-cell
-// candidate list, CandLists).  Reading past the end of the range (never past the array) is
-// harmless: whatever lies there is a real indexed point.
-PCR_HD void flat_eval(const GridView& G, FlatLane& L, int ch, const uint32_t* list_idx = nullptr, uint32_t list_last = 0u) {
+// candidate list, CandLists).  Groups of four may read past the end of the range: what lies there
+// is either another real indexed point (harmless: it can only win if it really is closer) or one
+// of the four sentinel records that terminate G.pts / list_idx (infinitely far, never win).
+PCR_HD void flat_eval(const GridView& G, FlatLane& L, int ch, const uint32_t* list_idx = nullptr) {
     const uint32_t avail = L.e - L.p;
     const uint32_t n = avail < (uint32_t)ch ? avail : (uint32_t)ch;
-    const uint32_t lastp = list_idx ? list_last : G.n_pts - 1u;
     for (uint32_t j = 0; j < n; j += 4) {
-        uint32_t p0 = L.p + j;
-        uint32_t p1 = p0 + 1u < lastp ? p0 + 1u : lastp, p2 = p0 + 2u < lastp ? p0 + 2u : lastp, p3 = p0 + 3u < lastp ? p0 + 3u : lastp;
+        uint32_t p0 = L.p + j, p1 = p0 + 1u, p2 = p0 + 2u, p3 = p0 + 3u;
         if (list_idx) { p0 = list_idx[p0]; p1 = list_idx[p1]; p2 = list_idx[p2]; p3 = list_idx[p3]; }
         const float4 t0 = G.pts[p0], t1 = G.pts[p1], t2 = G.pts[p2], t3 = G.pts[p3];
         float ex, ey, ez, d;

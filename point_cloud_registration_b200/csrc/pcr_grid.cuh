@@ -152,40 +152,12 @@ PCR_HD bool is_small_box(const Block3& b) {
     return (b.x1 - b.x0) <= 2 && (b.y1 - b.y0) <= 2 && (b.z1 - b.z0) <= 2;
 }
 
-// Generic exact search.  `best` carries the initial radius (max_dist^2) and receives results.
+// Second half of the exact search: the cells of `cur` have been visited, `best` holds what was
+// found there.  Grows the visited block ring by ring while nothing is known, then visits the cell
+// box of the ball (query, best) once.
 template <class Best>
-PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& best) {
-    if (G.n_pts == 0) return;
-    const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
-    if (!(gx == gx) || !(gy == gy) || !(gz == gz)) return;            // NaN query: no match
-    // distance from the query to the grid's bounding box; nothing can match beyond the radius
-    {
-        float ex = fmaxf(fmaxf(-gx, gx - (float)G.cnx), 0.0f);
-        float ey = fmaxf(fmaxf(-gy, gy - (float)G.cny), 0.0f);
-        float ez = fmaxf(fmaxf(-gz, gz - (float)G.cnz), 0.0f);
-        float e = fmaxf(sqrtf(ex * ex + ey * ey + ez * ez) - G.slack, 0.0f) * G.h;
-        if (e * e >= best.radius2()) return;
-    }
-    // clamp huge coordinates before the int conversion
+PCR_HD void grid_search_continue(const GridView& G, float qx, float qy, float qz, float gx, float gy, float gz, Block3 cur, Best& best) {
     const float big = 1.0e9f;
-    const float cgx = fminf(fmaxf(gx, -big), big), cgy = fminf(fmaxf(gy, -big), big), cgz = fminf(fmaxf(gz, -big), big);
-    Block3 cur;
-    Block3 none; none.x0 = none.y0 = none.z0 = 0; none.x1 = none.y1 = none.z1 = -1;
-    if (best.have()) {
-        // warm start: the caller already holds a candidate (an upper bound).  Every closer point
-        // lies in a cell meeting the ball (query, bound): visit exactly that box and stop.
-        const float r = sqrtf(best.radius2()) * G.inv_h * 1.000001f + G.slack;
-        cur.x0 = cell_of(fminf(fmaxf(gx - r, -big), big), G.cnx); cur.x1 = cell_of(fminf(fmaxf(gx + r, -big), big), G.cnx);
-        cur.y0 = cell_of(fminf(fmaxf(gy - r, -big), big), G.cny); cur.y1 = cell_of(fminf(fmaxf(gy + r, -big), big), G.cny);
-        cur.z0 = cell_of(fminf(fmaxf(gz - r, -big), big), G.cnz); cur.z1 = cell_of(fminf(fmaxf(gz + r, -big), big), G.cnz);
-        if (is_small_box(cur)) visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
-        else visit_block(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
-        return;
-    }
-    cur.x0 = cur.x1 = cell_of(cgx, G.cnx);
-    cur.y0 = cur.y1 = cell_of(cgy, G.cny);
-    cur.z0 = cur.z1 = cell_of(cgz, G.cnz);
-    visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
     for (;;) {
         // distance (grid units) from the query to the nearest face of the visited block that
         // still has unvisited grid cells behind it
@@ -224,12 +196,104 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
     }
 }
 
+// Generic exact search.  `best` carries the initial radius (max_dist^2) and receives results.
+template <class Best>
+PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& best) {
+    if (G.n_pts == 0) return;
+    const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
+    if (!(gx == gx) || !(gy == gy) || !(gz == gz)) return;            // NaN query: no match
+    // distance from the query to the grid's bounding box; nothing can match beyond the radius
+    {
+        float ex = fmaxf(fmaxf(-gx, gx - (float)G.cnx), 0.0f);
+        float ey = fmaxf(fmaxf(-gy, gy - (float)G.cny), 0.0f);
+        float ez = fmaxf(fmaxf(-gz, gz - (float)G.cnz), 0.0f);
+        float e = fmaxf(sqrtf(ex * ex + ey * ey + ez * ez) - G.slack, 0.0f) * G.h;
+        if (e * e >= best.radius2()) return;
+    }
+    // clamp huge coordinates before the int conversion
+    const float big = 1.0e9f;
+    const float cgx = fminf(fmaxf(gx, -big), big), cgy = fminf(fmaxf(gy, -big), big), cgz = fminf(fmaxf(gz, -big), big);
+    Block3 cur;
+    Block3 none; none.x0 = none.y0 = none.z0 = 0; none.x1 = none.y1 = none.z1 = -1;
+    if (best.have()) {
+        // warm start: the caller already holds a candidate (an upper bound).  Every closer point
+        // lies in a cell meeting the ball (query, bound): visit exactly that box and stop.
+        const float r = sqrtf(best.radius2()) * G.inv_h * 1.000001f + G.slack;
+        cur.x0 = cell_of(fminf(fmaxf(gx - r, -big), big), G.cnx); cur.x1 = cell_of(fminf(fmaxf(gx + r, -big), big), G.cnx);
+        cur.y0 = cell_of(fminf(fmaxf(gy - r, -big), big), G.cny); cur.y1 = cell_of(fminf(fmaxf(gy + r, -big), big), G.cny);
+        cur.z0 = cell_of(fminf(fmaxf(gz - r, -big), big), G.cnz); cur.z1 = cell_of(fminf(fmaxf(gz + r, -big), big), G.cnz);
+        if (is_small_box(cur)) visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+        else visit_block(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+        return;
+    }
+    cur.x0 = cur.x1 = cell_of(cgx, G.cnx);
+    cur.y0 = cur.y1 = cell_of(cgy, G.cny);
+    cur.z0 = cur.z1 = cell_of(cgz, G.cnz);
+    visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+    grid_search_continue(G, qx, qy, qz, gx, gy, gz, cur, best);
+}
+
 // 1-NN convenience wrapper: returns position in G.pts (or -1) and the squared distance.
 PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2, float& out_d2) {
     Best1 b; b.d2 = max_d2; b.pos = -1;
     grid_search(G, qx, qy, qz, b);
     out_d2 = b.d2;
     return b.pos;
+}
+
+// 1-NN through the per-cell neighbour lists (see NbrLists).  Returns false when the query's cell
+// has no list (the caller runs the general search from scratch).  Exact: every occupied cell of
+// the 3x3x3 block around the query's cell is either evaluated or pruned by its box distance; if
+// the ball of the best then leaves the block, grid_search_continue() covers the rest.
+PCR_HD bool nbr_nn(const GridView& G, const NbrLists& N, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
+    const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
+    if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) return false;
+    const int cx = (int)gx, cy = (int)gy, cz = (int)gz;
+    const uint4 rec = N.bricks[((size_t)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2)];
+    const unsigned long long band = ((unsigned long long)rec.y << 32) | rec.x;
+    const int bit = brick_bit(cx, cy, cz);
+    if (!((band >> bit) & 1ull)) return false;
+    const uint32_t ord = rec.z + (uint32_t)popc64(band & ((1ull << bit) - 1ull));
+    const uint32_t s = N.nstart[ord], e = N.nstart[ord + 1];
+    Best1 best; best.d2 = max_d2; best.pos = -1;
+    const float h2 = G.h * G.h;
+    // distance (grid units) from the query to the nearest face of its own cell: once the best is
+    // within it (less the slack) no other cell can hold a closer point
+    const float fx = gx - (float)cx, fy = gy - (float)cy, fz = gz - (float)cz;
+    const float own = fminf(fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy)), fminf(fz, 1.0f - fz)) - G.slack;
+    const float own2 = own > 0.0f ? own * own * h2 : 0.0f;
+    for (uint32_t k = s; k < e; ++k) {
+        const uint2 ent = N.entries[k];
+        const int code = (int)(ent.y >> 26);
+        const int ox = (code & 3) - 1, oy = ((code >> 2) & 3) - 1, oz = (code >> 4) - 1;
+        if (code != 21) {                                     // 21 = (1,1,1): the own cell is never pruned
+            if (best.d2 <= own2) break;                       // strict '<' offers: nothing outside the own cell can win
+            const float lx = (float)(cx + ox), ly = (float)(cy + oy), lz = (float)(cz + oz);
+            const float dx = fmaxf(fmaxf(lx - gx, gx - (lx + 1.0f)) - G.slack, 0.0f);
+            const float dy = fmaxf(fmaxf(ly - gy, gy - (ly + 1.0f)) - G.slack, 0.0f);
+            const float dz = fmaxf(fmaxf(lz - gz, gz - (lz + 1.0f)) - G.slack, 0.0f);
+            if ((dx * dx + dy * dy + dz * dz) * h2 >= best.d2) continue;
+        }
+        const uint32_t p0 = ent.x, n = ent.y & 0x3ffffffu;
+        // groups of four; the tail may read into the next cell or the sentinels behind the array
+        for (uint32_t j = 0; j < n; j += 4) {
+            const float4 t0 = G.pts[p0 + j], t1 = G.pts[p0 + j + 1], t2 = G.pts[p0 + j + 2], t3 = G.pts[p0 + j + 3];
+            float ex, ey, ez;
+            ex = t0.x - qx; ey = t0.y - qy; ez = t0.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j));
+            ex = t1.x - qx; ey = t1.y - qy; ez = t1.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j + 1));
+            ex = t2.x - qx; ey = t2.y - qy; ez = t2.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j + 2));
+            ex = t3.x - qx; ey = t3.y - qy; ez = t3.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j + 3));
+        }
+    }
+    // the 3x3x3 block (clipped to the grid) is settled; does the ball of the best stay inside it?
+    Block3 cur;
+    cur.x0 = cx > 0 ? cx - 1 : 0; cur.x1 = cx < G.cnx - 1 ? cx + 1 : cx;
+    cur.y0 = cy > 0 ? cy - 1 : 0; cur.y1 = cy < G.cny - 1 ? cy + 1 : cy;
+    cur.z0 = cz > 0 ? cz - 1 : 0; cur.z1 = cz < G.cnz - 1 ? cz + 1 : cz;
+    if (!(best.d2 <= own2)) grid_search_continue(G, qx, qy, qz, gx, gy, gz, cur, best);
+    out_d2 = best.d2;
+    out_pos = best.pos;
+    return true;
 }
 
 // 1-NN through the per-cell candidate lists (see CandLists); returns false when the query's cell

@@ -32,6 +32,8 @@ struct LinParams {
     const float4* vrec;                                  // VPLANE: 2 float4 / voxel, NDT: 3 float4 / voxel
     CandLists lists;                                     // VPLANE/NDT: per-cell candidate lists (null = absent)
     int use_lists;
+    NbrLists nbr;                                        // ICP/PLANE: per-cell neighbour lists (null = absent)
+    int use_nbr;
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
     float local_r1;           // tile kernel: warm-start radius (cells) up to which the per-lane local search is used
@@ -39,7 +41,6 @@ struct LinParams {
     int warm;                 // per-point kernel: use P.prev as warm start
     int flat_ch;              // flat kernel: candidates evaluated per lane and round
     int flat_tau;             // flat kernel: lanes that must be out of work before the warp looks for new cells
-    uint32_t list_last;       // last valid offset of lists.list_idx
     float r0_param;           // first search radius (grid units) when use_param_T; <= 0: take st->search_r0
     double T_param[16];
     int use_param_T;          // 1: transform comes from T_param, 0: from st->T (device loop)
@@ -257,6 +258,9 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_lane_kernel(const
         if ((METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT) && P.use_lists) {
             // voxel means: the query's cell carries the exact candidate list -- no search
             if (!list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos)) pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+        } else if ((METHOD == PCR_METHOD_ICP || METHOD == PCR_METHOD_PLANE) && P.use_nbr) {
+            // target points: candidate cells come from the neighbour list of the query's cell
+            if (!nbr_nn(P.grid, P.nbr, qx, qy, qz, P.max_d2, d2, pos)) pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
         } else {
             pos = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? P.prev[i] : -1, d2);
         }
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_flat_kernel(const
                     else { P.prev[i] = -1; i += stride; }
                 }
             }
-            flat_eval(P.grid, L, ch, (kLists && lmode) ? P.lists.list_idx : nullptr, P.list_last);
+            flat_eval(P.grid, L, ch, (kLists && lmode) ? P.lists.list_idx : nullptr);
         }
     }
 
@@ -600,11 +604,12 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.prev = ctx->scan_prev.as<int>();
     P.lists = ctx->vox_lists;
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
+    P.nbr = ctx->tgt_nbr;
+    P.use_nbr = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_nbr_lists && ctx->tgt_nbr.bricks != nullptr;
     P.local_r1 = ctx->local_r1;
     P.warm = ctx->warm_start;
     P.flat_ch = ctx->flat_ch;
     P.flat_tau = ctx->flat_tau;
-    P.list_last = ctx->n_list_entries > 0 ? (uint32_t)(ctx->n_list_entries - 1) : 0u;
     P.r0_min = ctx->r0_min;
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
     const float md = (float)max_dist;

@@ -21,6 +21,11 @@ struct HostGrid {
     std::vector<uint4> bricks;
     std::vector<uint32_t> cell_start;
     std::vector<float4> pts;
+    // per-cell neighbour lists (host mirror of build_nbr_lists in pcr_build.cu)
+    NbrLists nbr{};
+    std::vector<uint4> nbr_bricks;
+    std::vector<uint32_t> nbr_start;
+    std::vector<uint2> nbr_entries;
 };
 
 extern "C" {
@@ -74,6 +79,7 @@ void* hs_grid_build(const float* xyz, int64_t n, double h) {
         }
     }
     g->cell_start.push_back((uint32_t)n);
+    for (int k = 0; k < 4; ++k) g->pts.push_back(make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f));   // sentinels (see pad_tail_kernel)
     V.bricks = g->bricks.data(); V.cell_start = g->cell_start.data(); V.pts = g->pts.data();
     return g;
 }
@@ -111,6 +117,82 @@ void hs_knn(void* gp, const float* q, int64_t m, int k, int64_t* idx, float* dis
     }
 }
 
+
+
+// Host mirror of band_mark_kernel(dilate 1) + nbr_build_kernel: same band, same entry order.
+int64_t hs_nbr_build(void* gp) {
+    HostGrid* g = (HostGrid*)gp;
+    const GridView& G = g->v;
+    static const signed char order[27][3] = {
+        {0, 0, 0},
+        {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
+        {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}, {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1},
+        {-1, -1, -1}, {1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}, {1, 1, 1}};
+    const size_t nb = (size_t)G.bnx * G.bny * G.bnz;
+    std::vector<unsigned long long> band(nb, 0ull);
+    auto occupied = [&](int x, int y, int z, uint32_t* ord) {
+        const uint4 rec = g->bricks[((size_t)(z >> 2) * G.bny + (y >> 2)) * G.bnx + (x >> 2)];
+        const unsigned long long occ = ((unsigned long long)rec.y << 32) | rec.x;
+        const int bit = brick_bit(x, y, z);
+        if (!((occ >> bit) & 1ull)) return false;
+        if (ord) *ord = rec.z + (uint32_t)popc64(occ & ((1ull << bit) - 1ull));
+        return true;
+    };
+    for (int z = 0; z < G.cnz; ++z) for (int y = 0; y < G.cny; ++y) for (int x = 0; x < G.cnx; ++x) {
+        if (!occupied(x, y, z, nullptr)) continue;
+        for (int o = 0; o < 27; ++o) {
+            const int nx = x + order[o][0], ny = y + order[o][1], nz = z + order[o][2];
+            if (nx < 0 || ny < 0 || nz < 0 || nx >= G.cnx || ny >= G.cny || nz >= G.cnz) continue;
+            band[((size_t)(nz >> 2) * G.bny + (ny >> 2)) * G.bnx + (nx >> 2)] |= 1ull << brick_bit(nx, ny, nz);
+        }
+    }
+    g->nbr_bricks.assign(nb, make_uint4(0, 0, 0, 0));
+    g->nbr_start.clear(); g->nbr_entries.clear();
+    uint32_t ord = 0;
+    for (size_t b = 0; b < nb; ++b) {
+        g->nbr_bricks[b] = make_uint4((uint32_t)band[b], (uint32_t)(band[b] >> 32), ord, 0);
+        const int bx = (int)(b % G.bnx), by = (int)((b / G.bnx) % G.bny), bz = (int)(b / ((size_t)G.bnx * G.bny));
+        for (int bit = 0; bit < 64; ++bit) {
+            if (!((band[b] >> bit) & 1ull)) continue;
+            const int cx = bx * 4 + (bit & 3), cy = by * 4 + ((bit >> 2) & 3), cz = bz * 4 + (bit >> 4);
+            g->nbr_start.push_back((uint32_t)g->nbr_entries.size());
+            for (int o = 0; o < 27; ++o) {
+                const int dx = order[o][0], dy = order[o][1], dz = order[o][2];
+                const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+                if (nx < 0 || ny < 0 || nz < 0 || nx >= G.cnx || ny >= G.cny || nz >= G.cnz) continue;
+                uint32_t o2;
+                if (!occupied(nx, ny, nz, &o2)) continue;
+                const uint32_t s0 = g->cell_start[o2], e0 = g->cell_start[o2 + 1];
+                const uint32_t code = (uint32_t)((dx + 1) | ((dy + 1) << 2) | ((dz + 1) << 4));
+                g->nbr_entries.push_back(make_uint2(s0, (code << 26) | (e0 - s0)));
+            }
+            ++ord;
+        }
+    }
+    g->nbr_start.push_back((uint32_t)g->nbr_entries.size());
+    g->nbr.bricks = g->nbr_bricks.data(); g->nbr.nstart = g->nbr_start.data(); g->nbr.entries = g->nbr_entries.data();
+    return (int64_t)g->nbr_entries.size();
+}
+
+// 1-NN through the neighbour lists (general search when the cell has no list), as the kernel does.
+// used_list[i] = 1 when the list path answered.
+void hs_nbr_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, float* dist, uint8_t* used_list) {
+    HostGrid* g = (HostGrid*)gp;
+    const GridView& G = g->v;
+    const float md = (float)max_dist;
+    for (int64_t i = 0; i < m; ++i) {
+        float d2;
+        int pos;
+        const bool ok = nbr_nn(G, g->nbr, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
+        if (!ok) pos = grid_nn(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2);
+        if (used_list) used_list[i] = ok ? 1 : 0;
+        if (pos >= 0) {
+            uint32_t j;
+            memcpy(&j, &G.pts[pos].w, 4);
+            idx[i] = j; dist[i] = sqrtf(d2);
+        } else { idx[i] = -1; dist[i] = INFINITY; }
+    }
+}
 
 // Single-lane replay of the resumable search (pcr_flat_search.cuh).
 void hs_flat_nn(void* gp, const float* q, int64_t m, double max_dist, int ch, int64_t* idx, float* dist) {
@@ -221,6 +303,42 @@ void hs_flat_warp_sim(void* gp, const float* q, int64_t m, double max_dist, int 
             stats[5] += (double)b.evals;
         }
         stats[4] += (double)mx;
+    }
+}
+
+
+// Development aid: candidates evaluated per query by the flat search when the pruning radius
+// starts at (a) max_dist, (b) the true NN distance (perfect bound), (c) the distance to the NN of
+// the query's cell centre ("seed" bound).  out[3] = totals.
+void hs_bound_study(void* gp, const float* q, int64_t m, double max_dist, double* out) {
+    const GridView& G = ((HostGrid*)gp)->v;
+    const float md2 = (float)max_dist * (float)max_dist;
+    out[0] = out[1] = out[2] = 0;
+    for (int64_t i = 0; i < m; ++i) {
+        const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+        float d2true;
+        int pos = grid_nn(G, qx, qy, qz, md2, d2true);
+        // seed: NN of the centre of the query's cell
+        const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
+        const float cx = (floorf(gx) + 0.5f) * G.h + G.ox, cy = (floorf(gy) + 0.5f) * G.h + G.oy, cz = (floorf(gz) + 0.5f) * G.h + G.oz;
+        float dseed;
+        int spos = grid_nn(G, cx, cy, cz, 3.0e38f, dseed);
+        float seed_d2 = md2;
+        if (spos >= 0) {
+            const float4 t = G.pts[spos];
+            const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+            seed_d2 = std::min(md2, (ex * ex + ey * ey + ez * ez) * 1.00001f + 1e-12f);
+        }
+        const float starts[3] = {md2, pos >= 0 ? d2true * 1.00001f + 1e-12f : md2, seed_d2};
+        for (int v = 0; v < 3; ++v) {
+            FlatLane L;
+            long long cnt = 0;
+            if (flat_begin(G, L, qx, qy, qz, starts[v])) {
+                if (v > 0) L.best_pos = 0;     // pretend a candidate exists: the first pass after the own cell is the ball pass
+                while (flat_find_work(G, L)) { cnt += (L.e - L.p); flat_eval(G, L, 1 << 20); }
+            }
+            out[v] += (double)cnt;
+        }
     }
 }
 

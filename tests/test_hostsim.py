@@ -34,6 +34,9 @@ def hs():
     lib.hs_flat_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     lib.hs_flat_warp_sim.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_int]
+    lib.hs_nbr_build.restype = C.c_int64
+    lib.hs_nbr_build.argtypes = [C.c_void_p]
+    lib.hs_nbr_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.hs_linearize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_gn_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -157,6 +160,35 @@ def test_flat_search_matches_nested(hs, ch, tau, threads):
             assert np.array_equal(d0, d1) and np.array_equal(d0, d2)
             assert (i0 == i1).mean() > 0.999 and (i0 == i2).mean() > 0.999 and not np.any(i2 == -2)
             assert np.array_equal(i0 < 0, i1 < 0) and np.array_equal(i0 < 0, i2 < 0)
+        hs.hs_grid_free(g)
+
+
+def test_neighbour_lists_match_general_search(hs):
+    """nbr_nn (per-cell neighbour lists + early exit + continuation into the general search)
+    returns exactly what grid_search() returns, for every regime: on the surface, displaced by
+    about one cell, far away (no list), outside the grid, NaN, tight and huge max_dist."""
+    rng = np.random.default_rng(6)
+    pts = ds.make_urban_slab(20000, seed=7)
+    near = ds.perturb_scan(pts, seed=3)[:4001]
+    off = near[:1500] + np.array([0.1, -0.2, 0.25], dtype=np.float32)
+    far = near[:700] + np.array([0, 0, 3.0], dtype=np.float32)
+    box = (rng.random((800, 3)) * (pts.max(0) - pts.min(0) + 6) + pts.min(0) - 3).astype(np.float32)
+    bad = near[:40].copy()
+    bad[::5, 1] = np.nan
+    for h in (0.08, 0.3, 0.45, 1.5):
+        g = hs.hs_grid_build(ptr(pts), len(pts), float(h))
+        assert hs.hs_nbr_build(g) > 0
+        for q, md, expect_lists in ((near, 2.0, h >= 0.45), (near, 0.03, h >= 0.45), (off, 2.0, h >= 1.5), (far, 2.0, False), (far, 1e9, False),
+                                    (box, 2.0, False), (bad, 2.0, h >= 0.45), (pts[:2000], 1e30, True)):
+            q = np.ascontiguousarray(q)
+            i0 = np.empty(len(q), np.int64); d0 = np.empty(len(q), np.float32)
+            hs.hs_nn(g, ptr(q), len(q), float(md), ptr(i0), ptr(d0))
+            i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32); used = np.zeros(len(q), np.uint8)
+            hs.hs_nbr_nn(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1), ptr(used))
+            assert np.array_equal(d0, d1)
+            assert np.array_equal(i0 < 0, i1 < 0) and (i0 == i1).mean() > 0.999
+            if expect_lists:
+                assert used.mean() > 0.5
         hs.hs_grid_free(g)
 
 
