@@ -182,11 +182,13 @@ int pcr_set_search_mode(pcr_ctx* ctx, int mode, int ch, int tau);
  * (default on); 0 falls back to the general grid search everywhere (A/B and test hook). */
 int pcr_set_voxel_lists(pcr_ctx* ctx, int enable);
 int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
-/* Target-point correspondences (ICP / PlaneICP) enumerate their candidate cells through per-cell
- * neighbour lists built with the NN index (default on); 0 walks the brick grid instead (A/B and
- * test hook).  Same exact nearest neighbour either way. */
-int pcr_set_nbr_lists(pcr_ctx* ctx, int enable);
-int pcr_nbr_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
+/* Target-point correspondences (ICP / PlaneICP) are read from per-cell "shell lists" built with
+ * the NN index (every point within `margin` cell edges of the cell, ordered by its distance to
+ * the cell; default on, margin 2 reduced until the lists fit the memory cap); 0 walks the brick
+ * grid instead (A/B and test hook).  Same exact nearest neighbour either way.
+ * PCR_SHELL_LISTS=0 / PCR_SHELL_DMAX / PCR_SHELL_MAX_GIB tune the build. */
+int pcr_set_shell_lists(pcr_ctx* ctx, int enable);
+int pcr_shell_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries, double* margin_cells);
 /* Test hook: exact NN of every resident scan point (storage order; upload with sort <= 0 to keep
  * the caller's order) under transform T through the TILE-COOPERATIVE search, against the target
  * points (which = 0) or the kept voxel means (which = 1); r0 = first search radius in cells.

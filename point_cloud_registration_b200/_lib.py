@@ -55,8 +55,8 @@ SYMBOLS = {
     "pcr_linearize_async": (_i, [_vp, _i, _vp, _d, _i]),
     "pcr_set_tile_lanes": (_i, [_vp, _i]),
     "pcr_set_search_mode": (_i, [_vp, _i, _i, _i]),
-    "pcr_set_nbr_lists": (_i, [_vp, _i]),
-    "pcr_nbr_list_stats": (_i, [_vp, _vp, _vp]),
+    "pcr_set_shell_lists": (_i, [_vp, _i]),
+    "pcr_shell_list_stats": (_i, [_vp, _vp, _vp, _vp]),
     "pcr_debug_matches": (_i, [_vp, _i, _vp]),
     "pcr_set_voxel_lists": (_i, [_vp, _i]),
     "pcr_voxel_list_stats": (_i, [_vp, _pi64, _pi64]),
@@ -252,13 +252,13 @@ class Context:
     def set_tile_lanes(self, lanes):
         self._check(self._lib.pcr_set_tile_lanes(self._h, int(lanes)))
 
-    def set_nbr_lists(self, enable):
-        self._check(self._lib.pcr_set_nbr_lists(self._h, int(bool(enable))))
+    def set_shell_lists(self, enable):
+        self._check(self._lib.pcr_set_shell_lists(self._h, int(bool(enable))))
 
-    def nbr_list_stats(self):
-        a, b = C.c_int64(), C.c_int64()
-        self._check(self._lib.pcr_nbr_list_stats(self._h, C.byref(a), C.byref(b)))
-        return dict(band_cells=a.value, entries=b.value)
+    def shell_list_stats(self):
+        a, b, m = C.c_int64(), C.c_int64(), C.c_double()
+        self._check(self._lib.pcr_shell_list_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
+        return dict(band_cells=a.value, entries=b.value, margin_cells=m.value, bytes=b.value * 17)
 
     def set_search_mode(self, mode, ch=0, tau=0):
         """mode 0: nested per-lane search, 1: persistent-lane flat search (see pcr_b200.h)."""

@@ -604,8 +604,8 @@ static int voxel_front(pcr_ctx* ctx, const void* xyz, long long n, double voxel_
 // ---------------------------------------------------------------------------------------
 // per-cell candidate lists over the kept voxel means (see CandLists in pcr_common.cuh)
 // ---------------------------------------------------------------------------------------
-constexpr int kBandDilate = 2;     // cells within this Chebyshev distance of a kept voxel get a list
-constexpr int kListRadius = 3;     // list build looks at the (2R+1)^3 neighbourhood; exact while D_C < R
+// ctx->list_dilate (default 2): cells within this Chebyshev distance of a kept voxel get a list
+// ctx->list_radius (default 3): the build looks at the (2R+1)^3 neighbourhood; exact while D_C < R
 
 // mark the neighbourhood of every kept voxel as "band" (cells that get a list)
 __global__ void band_mark_kernel(GridView G, BrickRec* __restrict__ lbricks, int dilate) {
@@ -641,7 +641,8 @@ __global__ void brick_base_set_kernel(BrickRec* __restrict__ bricks, unsigned lo
 // by brick through the occupancy masks, so empty cells cost nothing.
 template <bool FILL>
 __global__ void list_build_kernel(GridView G, const BrickRec* __restrict__ lbricks, unsigned long long nbricks, float* __restrict__ D2s,
-                                  uint32_t* __restrict__ counts, const uint32_t* __restrict__ list_start, uint32_t* __restrict__ list_idx) {
+                                  uint32_t* __restrict__ counts, const uint32_t* __restrict__ list_start, uint32_t* __restrict__ list_idx,
+                                  int kListRadius) {
     const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long b = tid >> 6;
     const int bit = (int)(tid & 63ull);
@@ -719,7 +720,7 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     PCR_CUDA(ctx->vox_lbricks.ensure((size_t)nbricks * sizeof(BrickRec)));
     PCR_CUDA(cudaMemsetAsync(ctx->vox_lbricks.p, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
     BrickRec* lb = ctx->vox_lbricks.as<BrickRec>();
-    band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb, kBandDilate);
+    band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb, ctx->list_dilate);
     PCR_LAUNCH_CHECK();
     PCR_CUDA(ctx->tmp_a.ensure((size_t)(nbricks + 1) * 4 * 2));
     uint32_t* bcnt = ctx->tmp_a.as<uint32_t>();
@@ -741,7 +742,7 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     float* D2s = ctx->tmp_c.as<float>();
     PCR_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_band + 1) * 4, ctx->stream));
     const long long nthreads = (long long)nbricks * 64;
-    list_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, counts, nullptr, nullptr);
+    list_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, counts, nullptr, nullptr, ctx->list_radius);
     PCR_LAUNCH_CHECK();
     rc = exclusive_sum_u32(ctx, counts, ctx->vox_list_start.as<uint32_t>(), (long long)n_band + 1);
     if (rc) return rc;
@@ -752,7 +753,7 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(nullptr, (long long)G.n_pts, ctx->vox_list_idx.as<uint32_t>(), (long long)n_entries);
     PCR_LAUNCH_CHECK();
     list_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, nullptr, ctx->vox_list_start.as<uint32_t>(),
-                                                                               ctx->vox_list_idx.as<uint32_t>());
+                                                                               ctx->vox_list_idx.as<uint32_t>(), ctx->list_radius);
     PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->vox_lists.bricks = ctx->vox_lbricks.as<uint4>();
@@ -765,113 +766,183 @@ static int build_voxel_lists(pcr_ctx* ctx) {
 
 
 // ---------------------------------------------------------------------------------------
-// per-cell neighbour lists over the target-point grid (see NbrLists in pcr_common.cuh)
+// per-cell shell lists over the target-point grid (see ShellLists in pcr_common.cuh)
 // ---------------------------------------------------------------------------------------
-// visiting order of the 3x3x3 block: own cell, 6 face, 12 edge, 8 corner neighbours
-__constant__ signed char kNbrOrder[27][3] = {
-    {0, 0, 0},
-    {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
-    {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}, {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1},
-    {-1, -1, -1}, {1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}, {1, 1, 1}};
+// level j >= 1 holds margins in (frac[j-1], frac[j]] cell edges (cut at dmax); level 0 = the cell's own points
+__constant__ float kShellFrac[PCR_SHELL_LEVELS] = {0.0f, 0.03125f, 0.0625f, 0.125f, 0.1768f, 0.25f, 0.3536f, 0.5f, 0.7071f, 1.0f, 1.4142f, 2.0f};
 
-// One thread per (brick, bit) of the band.  FILL = false: counts[ordinal] = number of occupied
-// cells in the 3x3x3 block; FILL = true: write the entries (own cell first -- nbr_nn relies on it).
+// One thread per (brick, bit) of the band.  FILL = false: counts[ordinal] = list length padded to
+// a multiple of four; FILL = true: write the entries level by level, the sentinels and the
+// per-group margin bounds.  dmax <= R cell edges, so the (2R+1)^3 block holds every point within dmax.
 template <bool FILL>
-__global__ void nbr_build_kernel(GridView G, const BrickRec* __restrict__ nbricks_rec, unsigned long long nbricks,
-                                 uint32_t* __restrict__ counts, const uint32_t* __restrict__ nstart, uint2* __restrict__ entries,
-                                 int* __restrict__ overflow) {
+__global__ void shell_build_kernel(GridView G, const BrickRec* __restrict__ band, unsigned long long nbricks, float dmax, int R,
+                                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ start, float4* __restrict__ out,
+                                   float* __restrict__ margin2) {
     const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long b = tid >> 6;
     const int bit = (int)(tid & 63ull);
     if (b >= nbricks) return;
-    const BrickRec lr = nbricks_rec[b];
+    const BrickRec lr = band[b];
     if (!((lr.mask >> bit) & 1ull)) return;
     const uint32_t ord = lr.base + (uint32_t)__popcll(lr.mask & ((1ull << bit) - 1ull));
     const int bx = (int)(b % (unsigned long long)G.bnx), by = (int)((b / (unsigned long long)G.bnx) % (unsigned long long)G.bny),
               bz = (int)(b / ((unsigned long long)G.bnx * G.bny));
     const int cx = bx * 4 + (bit & 3), cy = by * 4 + ((bit >> 2) & 3), cz = bz * 4 + (bit >> 4);
-    uint32_t n_out = 0, w = FILL ? nstart[ord] : 0u;
-    long long cached = -1;
-    uint4 rec = make_uint4(0, 0, 0, 0);
-    for (int o = 0; o < 27; ++o) {
-        const int dx = kNbrOrder[o][0], dy = kNbrOrder[o][1], dz = kNbrOrder[o][2];
-        const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
-        if (nx < 0 || ny < 0 || nz < 0 || nx >= G.cnx || ny >= G.cny || nz >= G.cnz) continue;
-        const long long nbk = ((long long)(nz >> 2) * G.bny + (ny >> 2)) * G.bnx + (nx >> 2);
-        if (nbk != cached) { rec = G.bricks[nbk]; cached = nbk; }
-        const unsigned long long occ = ((unsigned long long)rec.y << 32) | rec.x;
-        const int nbit = brick_bit(nx, ny, nz);
-        if (!((occ >> nbit) & 1ull)) continue;
-        if (!FILL && o == 0) {                                // every occupied cell is some band cell's own cell
-            const uint32_t o2 = rec.z + (uint32_t)__popcll(occ & ((1ull << nbit) - 1ull));
-            if (G.cell_start[o2 + 1] - G.cell_start[o2] >= (1u << 26)) atomicOr(overflow, 1);   // entry format holds 26-bit counts
-        }
-        if (FILL) {
+    const float lox = G.ox + (float)cx * G.h, loy = G.oy + (float)cy * G.h, loz = G.oz + (float)cz * G.h;
+    const float hix = lox + G.h, hiy = loy + G.h, hiz = loz + G.h;
+    float lim2[PCR_SHELL_LEVELS];
+#pragma unroll
+    for (int l = 0; l < PCR_SHELL_LEVELS; ++l) lim2[l] = (kShellFrac[l] * G.h) * (kShellFrac[l] * G.h);
+    const float dmax2 = dmax * dmax;
+    uint32_t cnt[PCR_SHELL_LEVELS];
+#pragma unroll
+    for (int l = 0; l < PCR_SHELL_LEVELS; ++l) cnt[l] = 0u;
+    uint32_t base = FILL ? start[ord] : 0u;
+    for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
+        long long cached = -1;
+        uint4 rec = make_uint4(0, 0, 0, 0);
+        const int side = 2 * R + 1, ncell = side * side * side, centre = (ncell - 1) / 2;
+        for (int oo = 0; oo < ncell; ++oo) {
+            // own cell first, then the rest of the block in z, y, x order
+            const int o = oo == 0 ? centre : (oo <= centre ? oo - 1 : oo);
+            const int nx = cx + o % side - R, ny = cy + (o / side) % side - R, nz = cz + o / (side * side) - R;
+            if (nx < 0 || ny < 0 || nz < 0 || nx >= G.cnx || ny >= G.cny || nz >= G.cnz) continue;
+            const long long nbk = ((long long)(nz >> 2) * G.bny + (ny >> 2)) * G.bnx + (nx >> 2);
+            if (nbk != cached) { rec = G.bricks[nbk]; cached = nbk; }
+            const unsigned long long occ = ((unsigned long long)rec.y << 32) | rec.x;
+            const int nbit = brick_bit(nx, ny, nz);
+            if (!((occ >> nbit) & 1ull)) continue;
             const uint32_t o2 = rec.z + (uint32_t)__popcll(occ & ((1ull << nbit) - 1ull));
             const uint32_t s = G.cell_start[o2], e = G.cell_start[o2 + 1];
-            const uint32_t code = (uint32_t)((dx + 1) | ((dy + 1) << 2) | ((dz + 1) << 4));
-            entries[w++] = make_uint2(s, (code << 26) | (e - s));
+            for (uint32_t p = s; p < e; ++p) {
+                const float4 t = G.pts[p];
+                int lvl = 0;
+                if (oo != 0) {                                // the cell's own points are level 0 by definition
+                    const float mx = fmaxf(fmaxf(lox - t.x, t.x - hix), 0.0f), my = fmaxf(fmaxf(loy - t.y, t.y - hiy), 0.0f),
+                                mz = fmaxf(fmaxf(loz - t.z, t.z - hiz), 0.0f);
+                    const float m2 = mx * mx + my * my + mz * mz;
+                    if (m2 > dmax2) continue;                 // farther than dmax from the cell
+                    lvl = PCR_SHELL_LEVELS - 1;
+#pragma unroll
+                    for (int l = PCR_SHELL_LEVELS - 2; l >= 1; --l) if (m2 <= lim2[l]) lvl = l;
+                }
+                if (pass == 0) {
+#pragma unroll
+                    for (int l = 0; l < PCR_SHELL_LEVELS; ++l) if (l == lvl) cnt[l]++;
+                } else {
+                    uint32_t w = 0;
+#pragma unroll
+                    for (int l = 0; l < PCR_SHELL_LEVELS; ++l) if (l == lvl) w = cnt[l]++;
+                    out[base + w] = make_float4(t.x, t.y, t.z, __uint_as_float(p));
+                }
+            }
         }
-        ++n_out;
+        if (pass == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int l = 0; l < PCR_SHELL_LEVELS; ++l) total += cnt[l];
+            const uint32_t padded = (total + 3u) & ~3u;
+            if (!FILL) { counts[ord] = padded; return; }
+            // per-group lower bound of the squared margin (slack covers the query's binning error),
+            // then turn the level counts into write cursors for the second pass
+            const float slack_w = G.slack * G.h;
+            uint32_t lvl_end = 0;
+            int l_of = 0;
+            uint32_t ends[PCR_SHELL_LEVELS];
+#pragma unroll
+            for (int l = 0; l < PCR_SHELL_LEVELS; ++l) { lvl_end += cnt[l]; ends[l] = lvl_end; }
+            for (uint32_t g4 = 0; g4 < padded; g4 += 4) {
+                while (l_of < PCR_SHELL_LEVELS - 1 && g4 >= ends[l_of]) ++l_of;     // level of the group's first entry
+                float lb = 0.0f;
+                if (g4 >= total) lb = 3.0e38f;                                        // (cannot happen: groups start below total)
+                else if (l_of >= 1) lb = fmaxf(kShellFrac[l_of - 1] * G.h - slack_w, 0.0f);
+                margin2[(base + g4) >> 2] = lb * lb;
+            }
+            for (uint32_t k = total; k < padded; ++k) out[base + k] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, __uint_as_float(0xffffffffu));
+            uint32_t run = 0;
+#pragma unroll
+            for (int l = 0; l < PCR_SHELL_LEVELS; ++l) { const uint32_t c = cnt[l]; cnt[l] = run; run += c; }
+        }
     }
-    if (!FILL) counts[ord] = n_out;
 }
 
-static int build_nbr_lists(pcr_ctx* ctx) {
+static int build_shell_lists(pcr_ctx* ctx) {
     Grid& g = ctx->tgt_grid;
-    ctx->tgt_nbr = NbrLists{};
-    ctx->n_nbr_band = ctx->n_nbr_entries = 0;
+    ctx->tgt_shell = ShellLists{};
+    ctx->n_shell_band = ctx->n_shell_entries = 0;
+    ctx->shell_dmax_used = 0.0;
     if (!g.built || g.view.n_pts == 0) return PCR_OK;
-    if (const char* e = getenv("PCR_NBR_LISTS")) if (atoi(e) == 0) return PCR_OK;
+    if (const char* e = getenv("PCR_SHELL_LISTS")) if (atoi(e) == 0) return PCR_OK;
     const GridView& G = g.view;
     const unsigned long long nbricks = (unsigned long long)G.bnx * G.bny * G.bnz;
-    PCR_CUDA(ctx->nbr_bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
-    PCR_CUDA(cudaMemsetAsync(ctx->nbr_bricks.p, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
-    BrickRec* lb = ctx->nbr_bricks.as<BrickRec>();
-    band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb, 1);
-    PCR_LAUNCH_CHECK();
-    PCR_CUDA(ctx->tmp_a.ensure((size_t)(nbricks + 1) * 4 * 2));
-    uint32_t* bcnt = ctx->tmp_a.as<uint32_t>();
-    uint32_t* bbase = bcnt + (nbricks + 1);
-    PCR_CUDA(cudaMemsetAsync(bcnt, 0, (size_t)(nbricks + 1) * 4, ctx->stream));
-    brick_popc_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bcnt);
-    PCR_LAUNCH_CHECK();
-    int rc = exclusive_sum_u32(ctx, bcnt, bbase, (long long)nbricks + 1);
-    if (rc) return rc;
-    uint32_t n_band = 0;
-    PCR_CUDA(cudaMemcpyAsync(&n_band, bbase + nbricks, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-    brick_base_set_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bbase);
-    PCR_LAUNCH_CHECK();
-    PCR_CUDA(ctx->tmp_b.ensure(((size_t)n_band + 1) * 4));
-    PCR_CUDA(ctx->nbr_start.ensure(((size_t)n_band + 1) * 4));
-    uint32_t* counts = ctx->tmp_b.as<uint32_t>();
-    PCR_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_band + 1) * 4, ctx->stream));
+    PCR_CUDA(ctx->shell_bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
+    BrickRec* lb = ctx->shell_bricks.as<BrickRec>();
     const long long nthreads = (long long)nbricks * 64;
-    PCR_CUDA(ctx->tmp_e.ensure(64));
-    int* d_overflow = ctx->tmp_e.as<int>();
-    PCR_CUDA(cudaMemsetAsync(d_overflow, 0, 4, ctx->stream));
-    nbr_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, counts, nullptr, nullptr, d_overflow);
-    PCR_LAUNCH_CHECK();
-    rc = exclusive_sum_u32(ctx, counts, ctx->nbr_start.as<uint32_t>(), (long long)n_band + 1);
-    if (rc) return rc;
-    uint32_t n_entries = 0;
-    int overflow = 0;
-    PCR_CUDA(cudaMemcpyAsync(&n_entries, ctx->nbr_start.as<uint32_t>() + n_band, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaMemcpyAsync(&overflow, d_overflow, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (overflow) return PCR_OK;                              // a cell with >= 2^26 points: keep the general search
-    PCR_CUDA(ctx->nbr_entries.ensure(((size_t)n_entries + 1) * sizeof(uint2)));
-    nbr_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, nullptr, ctx->nbr_start.as<uint32_t>(),
-                                                                              ctx->nbr_entries.as<uint2>(), nullptr);
-    PCR_LAUNCH_CHECK();
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->tgt_nbr.bricks = ctx->nbr_bricks.as<uint4>();
-    ctx->tgt_nbr.nstart = ctx->nbr_start.as<uint32_t>();
-    ctx->tgt_nbr.entries = ctx->nbr_entries.as<uint2>();
-    ctx->n_nbr_band = n_band;
-    ctx->n_nbr_entries = n_entries;
-    return PCR_OK;
+    // the requested margin first, then smaller ones until the lists fit the memory cap
+    const double tries[4] = {ctx->shell_dmax_frac, 1.5, 1.0, 0.5};
+    for (int t = 0; t < 4; ++t) {
+        const double frac = tries[t];
+        if (t > 0 && frac >= tries[0]) continue;
+        const int R = frac <= 1.0 ? 1 : 2;                   // build neighbourhood and band dilation (cells)
+        const float dmax = (float)(frac * (double)G.h);
+        PCR_CUDA(cudaMemsetAsync(lb, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
+        band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb, R);
+        PCR_LAUNCH_CHECK();
+        PCR_CUDA(ctx->tmp_a.ensure((size_t)(nbricks + 1) * 4 * 2));
+        uint32_t* bcnt = ctx->tmp_a.as<uint32_t>();
+        uint32_t* bbase = bcnt + (nbricks + 1);
+        PCR_CUDA(cudaMemsetAsync(bcnt, 0, (size_t)(nbricks + 1) * 4, ctx->stream));
+        brick_popc_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bcnt);
+        PCR_LAUNCH_CHECK();
+        int rc = exclusive_sum_u32(ctx, bcnt, bbase, (long long)nbricks + 1);
+        if (rc) return rc;
+        uint32_t n_band = 0;
+        PCR_CUDA(cudaMemcpyAsync(&n_band, bbase + nbricks, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        brick_base_set_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bbase);
+        PCR_LAUNCH_CHECK();
+        PCR_CUDA(ctx->tmp_b.ensure(((size_t)n_band + 1) * 4));
+        PCR_CUDA(ctx->shell_start.ensure(((size_t)n_band + 1) * 4));
+        uint32_t* counts = ctx->tmp_b.as<uint32_t>();
+        PCR_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_band + 1) * 4, ctx->stream));
+        shell_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, dmax, R, counts, nullptr, nullptr, nullptr);
+        PCR_LAUNCH_CHECK();
+        // total size in 64 bits: the 32-bit offsets below must not wrap, and the lists must fit the cap
+        size_t tmp = 0;
+        PCR_CUDA(ctx->tmp_e.ensure(64));
+        unsigned long long* d_total = ctx->tmp_e.as<unsigned long long>();
+        PCR_CUDA(cub::DeviceReduce::Sum(nullptr, tmp, counts, d_total, (long long)n_band, ctx->stream));
+        PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+        PCR_CUDA(cub::DeviceReduce::Sum(ctx->cub_tmp.p, tmp, counts, d_total, (long long)n_band, ctx->stream));
+        ctx->launches += 1;
+        unsigned long long total = 0;
+        PCR_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double gib = (double)total * 17.0 / (1024.0 * 1024.0 * 1024.0);
+        if (total >= (1ull << 32) - 8ull || gib > ctx->shell_max_gib) continue;      // too large: try a smaller margin
+        rc = exclusive_sum_u32(ctx, counts, ctx->shell_start.as<uint32_t>(), (long long)n_band + 1);
+        if (rc) return rc;
+        const uint32_t n_entries = (uint32_t)total;
+        PCR_CUDA(ctx->shell_pts.ensure(((size_t)n_entries + 4) * sizeof(float4)));
+        PCR_CUDA(ctx->shell_margin2.ensure(((size_t)n_entries / 4 + 1) * 4));
+        pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(ctx->shell_pts.as<float4>(), (long long)n_entries, nullptr, 0);
+        PCR_LAUNCH_CHECK();
+        shell_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, dmax, R, nullptr, ctx->shell_start.as<uint32_t>(),
+                                                                                    ctx->shell_pts.as<float4>(), ctx->shell_margin2.as<float>());
+        PCR_LAUNCH_CHECK();
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->tgt_shell.bricks = ctx->shell_bricks.as<uint4>();
+        ctx->tgt_shell.start = ctx->shell_start.as<uint32_t>();
+        ctx->tgt_shell.pts = ctx->shell_pts.as<float4>();
+        ctx->tgt_shell.margin2 = ctx->shell_margin2.as<float>();
+        const float cov = fmaxf(dmax - G.slack * G.h, 0.0f);
+        ctx->tgt_shell.covered2 = cov * cov;
+        ctx->n_shell_band = n_band;
+        ctx->n_shell_entries = n_entries;
+        ctx->shell_dmax_used = frac;
+        return PCR_OK;
+    }
+    return PCR_OK;                                            // nothing fits: the general search stays in charge
 }
 
 template <typename T>
@@ -996,6 +1067,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&ctx->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         std::string m = std::string("pcr_create: ") + cudaGetErrorString(e);
         delete ctx;
@@ -1010,6 +1082,11 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_R0_MIN")) ctx->r0_min = (float)atof(e);
     if (const char* e = getenv("PCR_WARM")) ctx->warm_start = atoi(e);
     if (const char* e = getenv("PCR_LOCAL_R1")) ctx->local_r1 = (float)atof(e);
+    if (const char* e = getenv("PCR_SHELL_DMAX")) ctx->shell_dmax_frac = atof(e) > 0.0 && atof(e) <= 2.0 ? atof(e) : 1.0;
+    if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 24.0;
+    if (const char* e = getenv("PCR_QUEUE")) ctx->use_queue = atoi(e) != 0;
+    if (const char* e = getenv("PCR_LIST_DILATE")) ctx->list_dilate = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 2;
+    if (const char* e = getenv("PCR_LIST_RADIUS")) ctx->list_radius = atoi(e) >= 2 && atoi(e) <= 6 ? atoi(e) : 3;
     if (const char* e = getenv("PCR_SEARCH")) ctx->search_mode = (!strcmp(e, "flat") || atoi(e) == 1) ? 1 : 0;
     if (const char* e = getenv("PCR_FLAT_CH")) ctx->flat_ch = atoi(e) >= 4 ? atoi(e) : 32;
     if (const char* e = getenv("PCR_FLAT_TAU")) ctx->flat_tau = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : 1;
@@ -1028,7 +1105,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->vox_mean.release(); ctx->vox_cov.release(); ctx->vox_norm.release(); ctx->vox_icov.release(); ctx->vox_count.release();
     ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
     ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release();
-    ctx->nbr_bricks.release(); ctx->nbr_start.release(); ctx->nbr_entries.release();
+    ctx->shell_bricks.release(); ctx->shell_start.release(); ctx->shell_pts.release(); ctx->shell_margin2.release();
     ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();
     ctx->partials.release(); ctx->state.release();
     ctx->tmp_a.release(); ctx->tmp_b.release(); ctx->tmp_c.release(); ctx->tmp_d.release(); ctx->tmp_e.release(); ctx->cub_tmp.release();
@@ -1036,6 +1113,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCR_OK;
@@ -1046,8 +1124,8 @@ int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n) {
     if (!xyz || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_set_target_points: empty target");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->tgt_grid.release();
-    ctx->tgt_nbr = NbrLists{};                  // lists refer to the released grid
-    ctx->n_nbr_band = ctx->n_nbr_entries = 0;
+    ctx->tgt_shell = ShellLists{};              // lists refer to the released grid
+    ctx->n_shell_band = ctx->n_shell_entries = 0;
     ctx->has_normals = false;
     PCR_CUDA(ctx->tgt_xyz.ensure((size_t)n * 12));
     PCR_CUDA(cudaMemcpyAsync(ctx->tgt_xyz.p, xyz, (size_t)n * 12,
@@ -1064,7 +1142,7 @@ int pcr_build_nn_index(pcr_ctx* ctx) {
     ctx->tgt_grid_epoch++;
     int rc = build_point_grid(ctx, ctx->tgt_xyz.as<float>(), ctx->n_tgt, ctx->tgt_grid, nullptr);
     if (rc) return rc;
-    return build_nbr_lists(ctx);
+    return build_shell_lists(ctx);
 }
 
 int pcr_estimate_normals(pcr_ctx* ctx, int k) {
@@ -1231,16 +1309,17 @@ int pcr_set_voxel_lists(pcr_ctx* ctx, int enable) {
     return PCR_OK;
 }
 
-int pcr_set_nbr_lists(pcr_ctx* ctx, int enable) {
+int pcr_set_shell_lists(pcr_ctx* ctx, int enable) {
     if (!ctx) return PCR_ERR_ARG;
-    ctx->use_nbr_lists = enable ? 1 : 0;
+    ctx->use_shell_lists = enable ? 1 : 0;
     return PCR_OK;
 }
 
-int pcr_nbr_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries) {
+int pcr_shell_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries, double* margin_cells) {
     if (!ctx) return PCR_ERR_ARG;
-    if (band_cells) *band_cells = ctx->n_nbr_band;
-    if (entries) *entries = ctx->n_nbr_entries;
+    if (band_cells) *band_cells = ctx->n_shell_band;
+    if (entries) *entries = ctx->n_shell_entries;
+    if (margin_cells) *margin_cells = ctx->shell_dmax_used;
     return PCR_OK;
 }
 

@@ -148,19 +148,26 @@ struct CandLists {
     const uint32_t* list_idx;    // positions in GridView::pts
 };
 
-// Per-cell neighbour lists over the target-point grid: for every "band" cell C (a cell within
-// Chebyshev distance 1 of an occupied cell) the occupied cells of the 3x3x3 block around C, own
-// cell first, then face, edge and corner neighbours.  One entry = the neighbour's point range in
-// GridView::pts plus its offset from C:
-//     entries[k].x = first point,  entries[k].y = (code << 26) | count,
-//     code = (dx + 1) | (dy + 1) << 2 | (dz + 1) << 4
-// A query enumerates its candidate cells by reading this short list instead of walking brick
-// records and occupancy masks (the walk was ~2/3 of the search's instructions); if the ball of its
-// best match leaves the 3x3x3 block, or its cell has no list, the general search takes over.
-struct NbrLists {
+// Per-cell "shell lists" over the target-point grid.  For every band cell C (within Chebyshev
+// distance 1 of an occupied cell) ONE contiguous list holds every indexed point whose distance to
+// the box of C (its "margin") is <= dmax, ordered by margin level: level 0 = the points binned in
+// C itself, levels 1.. = shells of growing margin.  Entries are float4 (x, y, z, position of the
+// point in GridView::pts); lists are padded to a multiple of four with sentinels, and for every
+// group of four `margin2[group]` is a lower bound of the squared margin of the group's and of all
+// later entries.  A query in C then needs no geometry at all:
+//     for each group: if (margin2[group] >= best) stop;  evaluate the four entries
+// -- a point not yet looked at is at least its margin away from any location in C -- and every
+// query of one cell streams the SAME addresses for (nearly) the SAME number of steps, which is
+// what the per-lane searches over cell walks could not offer (10-13 active lanes per warp
+// instruction, the rest waiting for stragglers).  If the list ends while the best is still
+// farther than dmax, the general search takes over from that bound.
+#define PCR_SHELL_LEVELS 12
+struct ShellLists {
     const uint4* bricks;         // (band mask lo, hi, ordinal of first band cell, unused), brick layout of the grid
-    const uint32_t* nstart;      // [n_band + 1]
-    const uint2* entries;
+    const uint32_t* start;       // [n_band + 1], multiples of 4
+    const float4* pts;           // entries (+ 4 sentinels)
+    const float* margin2;        // [entries / 4]
+    float covered2;              // (dmax - slack)^2: a best within it after the whole list is final
 };
 
 PCR_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

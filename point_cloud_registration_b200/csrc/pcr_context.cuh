@@ -14,6 +14,7 @@ namespace pcr {
 constexpr int kMaxTrace = 256;          // per-iteration e2 trace capacity of the on-device GN loop
 constexpr int kLinThreads = 256;        // threads per block of the linearise kernels
 constexpr int kMaxLinBlocks = 148 * 8;  // upper bound on persistent grid size (partials buffer)
+constexpr int kQueueCap = 6144;         // per-block straggler queue of the linearise kernel (24 KB of shared memory)
 
 // Device-resident Gauss-Newton loop state (one per context).
 struct LoopState {
@@ -69,10 +70,14 @@ struct pcr_ctx {
     pcr::DevBuf tgt_nrm_sorted;   // float4[n], same order as tgt_grid.pts
     pcr::DevBuf tgt_nrm_orig;     // float[3n], caller order
     bool has_normals = false;
-    pcr::DevBuf nbr_bricks, nbr_start, nbr_entries;   // per-cell neighbour lists over the target grid
-    pcr::NbrLists tgt_nbr{};      // null pointers = not built
-    long long n_nbr_band = 0, n_nbr_entries = 0;
-    int use_nbr_lists = 1;
+    pcr::DevBuf shell_bricks, shell_start, shell_pts, shell_margin2;   // per-cell shell lists over the target grid
+    pcr::ShellLists tgt_shell{};  // null pointers = not built
+    long long n_shell_band = 0, n_shell_entries = 0;
+    int use_shell_lists = 1;
+    int use_queue = 1;            // linearise kernel: list misses go to the block queue (0: searched in place, A/B)
+    double shell_dmax_frac = 2.0; // requested list margin in cell edges (<= 2); reduced until the lists fit shell_max_gib
+    double shell_max_gib = 24.0;  // memory cap of the lists
+    double shell_dmax_used = 0.0; // margin actually built (0: no lists)
 
     // ---- voxel statistics (VPlaneICP / NDT / VoxelGrid facade) ----
     long long n_vox = 0;          // kept voxels
@@ -84,6 +89,7 @@ struct pcr_ctx {
     pcr::CandLists vox_lists{};   // null pointers = not built
     long long n_band_cells = 0, n_list_entries = 0;
     int use_voxel_lists = 1;
+    int list_dilate = 2, list_radius = 3;   // candidate-list band dilation / build neighbourhood radius (cells)
     pcr::DevBuf vox_rec_plane;    // float4[2n]: (mean, 0), (normal, 0)
     pcr::DevBuf vox_rec_ndt;      // float4[3n]: (mean, W00), (W01, W02, W11, W12), (W22, 0, 0, 0)
     bool has_voxels = false, has_icov = false;
@@ -116,6 +122,7 @@ struct pcr_ctx {
     double* h_out = nullptr;             // pinned + mapped: rec[32] + T[16] + {iter, done} written by the kernel
     double* d_out_mapped = nullptr;      // device alias of h_out
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_copy = nullptr;       // host->device scan copy finished (the caller may reuse its buffer)
     float last_ms = 0.f;
     long long launches = 0;       // kernels launched by this context (all kinds)
 

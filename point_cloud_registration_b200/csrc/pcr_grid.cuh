@@ -14,6 +14,7 @@
 // current best, and the search stops only when the unvisited space is farther than the
 // best (or than max_dist, quirk Q4: a strict `dist < max_dist` bounds the search).
 #pragma once
+#include <cstring>
 #include "pcr_common.cuh"
 
 namespace pcr {
@@ -241,58 +242,59 @@ PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2
     return b.pos;
 }
 
-// 1-NN through the per-cell neighbour lists (see NbrLists).  Returns false when the query's cell
-// has no list (the caller runs the general search from scratch).  Exact: every occupied cell of
-// the 3x3x3 block around the query's cell is either evaluated or pruned by its box distance; if
-// the ball of the best then leaves the block, grid_search_continue() covers the rest.
-PCR_HD bool nbr_nn(const GridView& G, const NbrLists& N, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
+// Stream the shell list (see ShellLists) of the query's cell.  Returns
+//   0  the cell has no list: nothing was looked at, the caller must run the general search;
+//   1  final: out_d2 / out_pos hold the exact nearest neighbour (or -1: none within max_dist);
+//   2  list exhausted while the best is still beyond the covered margin: out_* hold an upper
+//      bound and the general search has to finish the job.
+PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
     const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
-    if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) return false;
+    if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) return 0;
     const int cx = (int)gx, cy = (int)gy, cz = (int)gz;
-    const uint4 rec = N.bricks[((size_t)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2)];
+    const uint4 rec = S.bricks[((size_t)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2)];
     const unsigned long long band = ((unsigned long long)rec.y << 32) | rec.x;
     const int bit = brick_bit(cx, cy, cz);
-    if (!((band >> bit) & 1ull)) return false;
+    if (!((band >> bit) & 1ull)) return 0;
     const uint32_t ord = rec.z + (uint32_t)popc64(band & ((1ull << bit) - 1ull));
-    const uint32_t s = N.nstart[ord], e = N.nstart[ord + 1];
-    Best1 best; best.d2 = max_d2; best.pos = -1;
-    const float h2 = G.h * G.h;
-    // distance (grid units) from the query to the nearest face of its own cell: once the best is
-    // within it (less the slack) no other cell can hold a closer point
-    const float fx = gx - (float)cx, fy = gy - (float)cy, fz = gz - (float)cz;
-    const float own = fminf(fminf(fminf(fx, 1.0f - fx), fminf(fy, 1.0f - fy)), fminf(fz, 1.0f - fz)) - G.slack;
-    const float own2 = own > 0.0f ? own * own * h2 : 0.0f;
-    for (uint32_t k = s; k < e; ++k) {
-        const uint2 ent = N.entries[k];
-        const int code = (int)(ent.y >> 26);
-        const int ox = (code & 3) - 1, oy = ((code >> 2) & 3) - 1, oz = (code >> 4) - 1;
-        if (code != 21) {                                     // 21 = (1,1,1): the own cell is never pruned
-            if (best.d2 <= own2) break;                       // strict '<' offers: nothing outside the own cell can win
-            const float lx = (float)(cx + ox), ly = (float)(cy + oy), lz = (float)(cz + oz);
-            const float dx = fmaxf(fmaxf(lx - gx, gx - (lx + 1.0f)) - G.slack, 0.0f);
-            const float dy = fmaxf(fmaxf(ly - gy, gy - (ly + 1.0f)) - G.slack, 0.0f);
-            const float dz = fmaxf(fmaxf(lz - gz, gz - (lz + 1.0f)) - G.slack, 0.0f);
-            if ((dx * dx + dy * dy + dz * dz) * h2 >= best.d2) continue;
-        }
-        const uint32_t p0 = ent.x, n = ent.y & 0x3ffffffu;
-        // groups of four; the tail may read into the next cell or the sentinels behind the array
-        for (uint32_t j = 0; j < n; j += 4) {
-            const float4 t0 = G.pts[p0 + j], t1 = G.pts[p0 + j + 1], t2 = G.pts[p0 + j + 2], t3 = G.pts[p0 + j + 3];
-            float ex, ey, ez;
-            ex = t0.x - qx; ey = t0.y - qy; ez = t0.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j));
-            ex = t1.x - qx; ey = t1.y - qy; ez = t1.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j + 1));
-            ex = t2.x - qx; ey = t2.y - qy; ez = t2.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j + 2));
-            ex = t3.x - qx; ey = t3.y - qy; ez = t3.z - qz; best.offer(ex * ex + ey * ey + ez * ez, (int)(p0 + j + 3));
-        }
+    const uint32_t s = S.start[ord], e = S.start[ord + 1];
+    float best = max_d2;
+    float best_w = 0.0f;
+    bool have = false;
+    uint32_t k = s;
+    for (; k < e; k += 4) {
+        if (S.margin2[k >> 2] >= best) break;                 // everything from here on is at least this far
+        const float4 t0 = S.pts[k], t1 = S.pts[k + 1], t2 = S.pts[k + 2], t3 = S.pts[k + 3];
+        float ex, ey, ez, d;
+        ex = t0.x - qx; ey = t0.y - qy; ez = t0.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = t0.w; have = true; }
+        ex = t1.x - qx; ey = t1.y - qy; ez = t1.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = t1.w; have = true; }
+        ex = t2.x - qx; ey = t2.y - qy; ez = t2.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = t2.w; have = true; }
+        ex = t3.x - qx; ey = t3.y - qy; ez = t3.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = t3.w; have = true; }
     }
-    // the 3x3x3 block (clipped to the grid) is settled; does the ball of the best stay inside it?
-    Block3 cur;
-    cur.x0 = cx > 0 ? cx - 1 : 0; cur.x1 = cx < G.cnx - 1 ? cx + 1 : cx;
-    cur.y0 = cy > 0 ? cy - 1 : 0; cur.y1 = cy < G.cny - 1 ? cy + 1 : cy;
-    cur.z0 = cz > 0 ? cz - 1 : 0; cur.z1 = cz < G.cnz - 1 ? cz + 1 : cz;
-    if (!(best.d2 <= own2)) grid_search_continue(G, qx, qy, qz, gx, gy, gz, cur, best);
-    out_d2 = best.d2;
-    out_pos = best.pos;
+    out_d2 = best;
+#if defined(__CUDA_ARCH__)
+    out_pos = have ? __float_as_int(best_w) : -1;
+#else
+    { int w; memcpy(&w, &best_w, 4); out_pos = have ? w : -1; }
+#endif
+    // stopped by a margin bound: final.  List exhausted: final only if the best (or, with no
+    // candidate, the search radius) lies within the covered margin.
+    return (k >= e && !(best <= S.covered2)) ? 2 : 1;
+}
+
+// 1-NN through the shell lists with the general search as continuation (host replay, and the
+// kernels' inline path when the straggler queue is full or disabled).  false: the cell has no list.
+PCR_HD bool shell_nn(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
+    const int st = shell_scan(G, S, qx, qy, qz, max_d2, out_d2, out_pos);
+    if (st == 0) return false;
+    if (st == 2) {
+        Best1 b; b.d2 = out_d2; b.pos = out_pos;
+        grid_search(G, qx, qy, qz, b);                        // warm start from the list's bound
+        out_d2 = b.d2; out_pos = b.pos;
+    }
     return true;
 }
 

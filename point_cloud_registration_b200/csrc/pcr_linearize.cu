@@ -32,8 +32,9 @@ struct LinParams {
     const float4* vrec;                                  // VPLANE: 2 float4 / voxel, NDT: 3 float4 / voxel
     CandLists lists;                                     // VPLANE/NDT: per-cell candidate lists (null = absent)
     int use_lists;
-    NbrLists nbr;                                        // ICP/PLANE: per-cell neighbour lists (null = absent)
-    int use_nbr;
+    ShellLists shell;                                    // ICP/PLANE: per-cell shell lists (null = absent)
+    int use_shell;
+    int use_queue;                                       // park list misses in the block queue (pass 1b) instead of searching in place
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
     float local_r1;           // tile kernel: warm-start radius (cells) up to which the per-lane local search is used
@@ -242,30 +243,70 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_tile_kernel(const
 template <int METHOD, int MINB>
 __global__ void __launch_bounds__(kLinThreads, MINB) linearize_lane_kernel(const LinParams P) {
     constexpr int NACC = NAcc<METHOD>::value;
+    constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
     __shared__ BlockShared sh;
+    __shared__ int sq[kQueueCap];                        // scan slots whose correspondence needs the general search
+    __shared__ int sq_len;
     Pose32 pose;
     float r0;
+    if (threadIdx.x == 0) sq_len = 0;
     if (!load_pose(P, sh, pose, r0)) return;
     const long long stride = (long long)gridDim.x * kLinThreads;
     const long long first = blockIdx.x * (long long)kLinThreads + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const bool lists = kVoxel ? (P.use_lists != 0) : (P.use_shell != 0);
 
-    for (long long i = first; i < P.n_pad; i += stride) {
+    // Pass 1a: every query streams the list of its cell (voxel means: exact candidate list; target
+    // points: margin-ordered shell list) -- lanes of one cell read the same addresses for nearly the
+    // same number of steps.  The few queries a list cannot settle (no list for the cell, or the
+    // best still beyond the listed margin) are NOT searched here, where they would stall the other
+    // 31 lanes of their warp: their slots go to a block queue ...
+    for (long long i = first; i < P.n_pad; i += stride) {       // n_pad and stride are multiples of 32: warps stay whole
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
         float d2;
-        int pos;
-        if ((METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT) && P.use_lists) {
-            // voxel means: the query's cell carries the exact candidate list -- no search
-            if (!list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos)) pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
-        } else if ((METHOD == PCR_METHOD_ICP || METHOD == PCR_METHOD_PLANE) && P.use_nbr) {
-            // target points: candidate cells come from the neighbour list of the query's cell
-            if (!nbr_nn(P.grid, P.nbr, qx, qy, qz, P.max_d2, d2, pos)) pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+        int pos = -1;
+        bool pending = false;
+        if (lists) {
+            if (px == px) {                                      // NaN = padding: no match
+                if (kVoxel) pending = !list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
+                else pending = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) != 1;
+            }
+            if (P.use_queue) {
+                const unsigned m = __ballot_sync(0xffffffffu, pending);
+                if (m) {
+                    const int leader = __ffs(m) - 1;
+                    int base = 0;
+                    if (lane == leader) base = atomicAdd(&sq_len, __popc(m));
+                    base = __shfl_sync(0xffffffffu, base, leader);
+                    if (pending) {
+                        const int slot = base + __popc(m & ((1u << lane) - 1u));
+                        if (slot < kQueueCap) sq[slot] = (int)i;
+                        else pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);     // queue full: search in place
+                    }
+                }
+            } else if (pending) {
+                pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+            }
         } else {
             pos = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? P.prev[i] : -1, d2);
         }
         P.prev[i] = pos;
     }
+    // ... Pass 1b: and the block works the queue off with every lane busy.
+    __syncthreads();
+    {
+        const int nq = sq_len < kQueueCap ? sq_len : kQueueCap;
+        for (int k = threadIdx.x; k < nq; k += kLinThreads) {
+            const long long i = sq[k];
+            const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+            float qx, qy, qz, d2;
+            transform32(pose, px, py, pz, qx, qy, qz);
+            P.prev[i] = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+        }
+    }
+    __syncthreads();                                             // queue results were parked by other threads of this block
 
     float acc[NACC + 1];
 #pragma unroll
@@ -344,7 +385,7 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_flat_kernel(const
 #pragma unroll
     for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
     for (long long i = first; i < P.n_pad; i += stride) {
-        const int pos = P.prev[i];                       // written by this very thread in pass 1
+        const int pos = P.prev[i];                       // parked in pass 1 by this block
         if (pos < 0) continue;
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
@@ -429,10 +470,20 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {
     return v;
 }
 
-__global__ void morton_key_kernel(const float* __restrict__ xyz, long long n, float ox, float oy, float oz, float scale,
+// mm = {min x, y, z, max x, y, z} as order-preserving ints (scan_bbox_kernel); read on the device
+// so that the upload needs no host round trip between the bounding box and the sort keys.
+__device__ __forceinline__ float ord2f_dev(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void morton_key_kernel(const float* __restrict__ xyz, long long n, const int* __restrict__ mm,
                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
+    float ox = 0.f, oy = 0.f, oz = 0.f, scale = 0.f;
+    if (mm[0] != INT_MAX) {                                   // at least one finite point
+        ox = ord2f_dev(mm[0]); oy = ord2f_dev(mm[1]); oz = ord2f_dev(mm[2]);
+        const float ext = fmaxf(fmaxf(ord2f_dev(mm[3]) - ox, ord2f_dev(mm[4]) - oy), ord2f_dev(mm[5]) - oz);
+        scale = ext > 0.f ? 1023.999f / ext : 0.f;
+    }
     float fx = (xyz[3 * i] - ox) * scale, fy = (xyz[3 * i + 1] - oy) * scale, fz = (xyz[3 * i + 2] - oz) * scale;
     uint32_t ix = (uint32_t)fminf(fmaxf(fx == fx ? fx : 0.f, 0.f), 1023.f);
     uint32_t iy = (uint32_t)fminf(fmaxf(fy == fy ? fy : 0.f, 0.f), 1023.f);
@@ -484,13 +535,6 @@ __global__ void scan_bbox_kernel(const float* __restrict__ xyz, long long n, int
 __global__ void mm_init_kernel(int* mm) {
     if (threadIdx.x < 3) mm[threadIdx.x] = INT_MAX;
     else if (threadIdx.x < 6) mm[threadIdx.x] = INT_MIN;
-}
-
-static inline float ord2f(int i) {
-    int j = i >= 0 ? i : i ^ 0x7fffffff;
-    float f;
-    memcpy(&f, &j, 4);
-    return f;
 }
 
 int ensure_loop_buffers(pcr_ctx* ctx) {
@@ -604,8 +648,9 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.prev = ctx->scan_prev.as<int>();
     P.lists = ctx->vox_lists;
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
-    P.nbr = ctx->tgt_nbr;
-    P.use_nbr = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_nbr_lists && ctx->tgt_nbr.bricks != nullptr;
+    P.shell = ctx->tgt_shell;
+    P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
+    P.use_queue = ctx->use_queue;
     P.local_r1 = ctx->local_r1;
     P.warm = ctx->warm_start;
     P.flat_ch = ctx->flat_ch;
@@ -698,11 +743,13 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
 
     if (n == 0) return PCR_OK;
     const float* d_xyz;
-    if (is_device_pointer(xyz)) {
+    const bool from_host = !is_device_pointer(xyz);
+    if (!from_host) {
         d_xyz = xyz;
     } else {
         PCR_CUDA(ctx->scan_raw.ensure((size_t)n * 12));
         PCR_CUDA(cudaMemcpyAsync(ctx->scan_raw.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        PCR_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
         d_xyz = ctx->scan_raw.as<float>();
     }
     const size_t pad_bytes = (size_t)ctx->n_scan_pad * 4;
@@ -720,34 +767,30 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
         int nb = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
         scan_bbox_kernel<<<nb, 256, 0, ctx->stream>>>(d_xyz, n, d_mm);
         PCR_LAUNCH_CHECK();
-        int h_mm[6];
-        PCR_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
-        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-        if (h_mm[0] != INT_MAX) {
-            float lo[3], ext = 0.f;
-            for (int a = 0; a < 3; ++a) { lo[a] = ord2f(h_mm[a]); ext = std::max(ext, ord2f(h_mm[3 + a]) - lo[a]); }
-            const float scale = ext > 0.f ? 1023.999f / ext : 0.f;
-            PCR_CUDA(ctx->tmp_c.ensure((size_t)n * 4 * 2));
-            PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
-            uint32_t* k_in = ctx->tmp_c.as<uint32_t>(); uint32_t* k_out = k_in + n;
-            uint32_t* v_in = ctx->tmp_d.as<uint32_t>(); uint32_t* v_out = v_in + n;
-            morton_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, lo[0], lo[1], lo[2], scale, k_in, v_in);
-            PCR_LAUNCH_CHECK();
-            size_t tmp = 0;
-            PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
-            PCR_CUDA(ctx->cub_tmp.ensure(tmp));
-            PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
-            ctx->launches += 4;
-            order = v_out;
-            ctx->scan_sorted = true;
-        }
+        PCR_CUDA(ctx->tmp_c.ensure((size_t)n * 4 * 2));
+        PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
+        uint32_t* k_in = ctx->tmp_c.as<uint32_t>(); uint32_t* k_out = k_in + n;
+        uint32_t* v_in = ctx->tmp_d.as<uint32_t>(); uint32_t* v_out = v_in + n;
+        morton_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, d_mm, k_in, v_in);
+        PCR_LAUNCH_CHECK();
+        size_t tmp = 0;
+        PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
+        PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+        PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
+        ctx->launches += 4;
+        order = v_out;
+        ctx->scan_sorted = true;
     }
     if (sort < 0) ctx->scan_sorted = true;      // caller promises a spatially coherent order
     scan_to_soa_kernel<<<(unsigned)((ctx->n_scan_pad + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, order, n, ctx->n_scan_pad,
                                                                                          ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
                                                                                          ctx->scan_z.as<float>());
     PCR_LAUNCH_CHECK();
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    // Host source: return as soon as the caller's buffer has been read; sort and re-layout keep
+    // running on the stream (every consumer is stream-ordered behind them).  Device source: the
+    // caller's array must stay untouched until the re-layout has read it, so wait for the stream.
+    if (from_host) PCR_CUDA(cudaEventSynchronize(ctx->ev_copy));
+    else PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     return PCR_OK;
 }
 

@@ -21,11 +21,12 @@ struct HostGrid {
     std::vector<uint4> bricks;
     std::vector<uint32_t> cell_start;
     std::vector<float4> pts;
-    // per-cell neighbour lists (host mirror of build_nbr_lists in pcr_build.cu)
-    NbrLists nbr{};
-    std::vector<uint4> nbr_bricks;
-    std::vector<uint32_t> nbr_start;
-    std::vector<uint2> nbr_entries;
+    // per-cell shell lists (host mirror of build_shell_lists in pcr_build.cu)
+    ShellLists shell{};
+    std::vector<uint4> shell_bricks;
+    std::vector<uint32_t> shell_start;
+    std::vector<float4> shell_pts;
+    std::vector<float> shell_margin2;
 };
 
 extern "C" {
@@ -119,8 +120,8 @@ void hs_knn(void* gp, const float* q, int64_t m, int k, int64_t* idx, float* dis
 
 
 
-// Host mirror of band_mark_kernel(dilate 1) + nbr_build_kernel: same band, same entry order.
-int64_t hs_nbr_build(void* gp) {
+// Host mirror of band_mark_kernel(dilate 1) + shell_build_kernel: same band, levels, layout.
+int64_t hs_shell_build(void* gp, double dmax_frac) {
     HostGrid* g = (HostGrid*)gp;
     const GridView& G = g->v;
     static const signed char order[27][3] = {
@@ -128,6 +129,10 @@ int64_t hs_nbr_build(void* gp) {
         {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
         {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}, {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1},
         {-1, -1, -1}, {1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}, {1, 1, 1}};
+    static const float frac[PCR_SHELL_LEVELS] = {0.0f, 0.03125f, 0.0625f, 0.125f, 0.1768f, 0.25f, 0.3536f, 0.5f, 0.7071f, 1.0f, 1.4142f, 2.0f};
+    const int R = dmax_frac <= 1.0 ? 1 : 2;
+    const int side = 2 * R + 1, ncell = side * side * side, centre = (ncell - 1) / 2;
+    const float dmax = (float)(dmax_frac * (double)G.h);
     const size_t nb = (size_t)G.bnx * G.bny * G.bnz;
     std::vector<unsigned long long> band(nb, 0ull);
     auto occupied = [&](int x, int y, int z, uint32_t* ord) {
@@ -140,50 +145,85 @@ int64_t hs_nbr_build(void* gp) {
     };
     for (int z = 0; z < G.cnz; ++z) for (int y = 0; y < G.cny; ++y) for (int x = 0; x < G.cnx; ++x) {
         if (!occupied(x, y, z, nullptr)) continue;
-        for (int o = 0; o < 27; ++o) {
-            const int nx = x + order[o][0], ny = y + order[o][1], nz = z + order[o][2];
+        for (int dz = -R; dz <= R; ++dz) for (int dy = -R; dy <= R; ++dy) for (int dx = -R; dx <= R; ++dx) {
+            const int nx = x + dx, ny = y + dy, nz = z + dz;
             if (nx < 0 || ny < 0 || nz < 0 || nx >= G.cnx || ny >= G.cny || nz >= G.cnz) continue;
             band[((size_t)(nz >> 2) * G.bny + (ny >> 2)) * G.bnx + (nx >> 2)] |= 1ull << brick_bit(nx, ny, nz);
         }
     }
-    g->nbr_bricks.assign(nb, make_uint4(0, 0, 0, 0));
-    g->nbr_start.clear(); g->nbr_entries.clear();
+    g->shell_bricks.assign(nb, make_uint4(0, 0, 0, 0));
+    g->shell_start.clear(); g->shell_pts.clear(); g->shell_margin2.clear();
+    const float slack_w = G.slack * G.h;
     uint32_t ord = 0;
     for (size_t b = 0; b < nb; ++b) {
-        g->nbr_bricks[b] = make_uint4((uint32_t)band[b], (uint32_t)(band[b] >> 32), ord, 0);
+        g->shell_bricks[b] = make_uint4((uint32_t)band[b], (uint32_t)(band[b] >> 32), ord, 0);
         const int bx = (int)(b % G.bnx), by = (int)((b / G.bnx) % G.bny), bz = (int)(b / ((size_t)G.bnx * G.bny));
         for (int bit = 0; bit < 64; ++bit) {
             if (!((band[b] >> bit) & 1ull)) continue;
             const int cx = bx * 4 + (bit & 3), cy = by * 4 + ((bit >> 2) & 3), cz = bz * 4 + (bit >> 4);
-            g->nbr_start.push_back((uint32_t)g->nbr_entries.size());
-            for (int o = 0; o < 27; ++o) {
-                const int dx = order[o][0], dy = order[o][1], dz = order[o][2];
-                const int nx = cx + dx, ny = cy + dy, nz = cz + dz;
+            const float lox = G.ox + (float)cx * G.h, loy = G.oy + (float)cy * G.h, loz = G.oz + (float)cz * G.h;
+            const float hix = lox + G.h, hiy = loy + G.h, hiz = loz + G.h;
+            std::vector<float4> lv[PCR_SHELL_LEVELS];
+            for (int oo = 0; oo < ncell; ++oo) {
+                const int o = oo == 0 ? centre : (oo <= centre ? oo - 1 : oo);
+                const int nx = cx + o % side - R, ny = cy + (o / side) % side - R, nz = cz + o / (side * side) - R;
                 if (nx < 0 || ny < 0 || nz < 0 || nx >= G.cnx || ny >= G.cny || nz >= G.cnz) continue;
                 uint32_t o2;
                 if (!occupied(nx, ny, nz, &o2)) continue;
-                const uint32_t s0 = g->cell_start[o2], e0 = g->cell_start[o2 + 1];
-                const uint32_t code = (uint32_t)((dx + 1) | ((dy + 1) << 2) | ((dz + 1) << 4));
-                g->nbr_entries.push_back(make_uint2(s0, (code << 26) | (e0 - s0)));
+                for (uint32_t p = g->cell_start[o2]; p < g->cell_start[o2 + 1]; ++p) {
+                    const float4 t = g->pts[p];
+                    int lvl = 0;
+                    if (oo != 0) {
+                        const float mx = fmaxf(fmaxf(lox - t.x, t.x - hix), 0.0f), my = fmaxf(fmaxf(loy - t.y, t.y - hiy), 0.0f),
+                                    mz = fmaxf(fmaxf(loz - t.z, t.z - hiz), 0.0f);
+                        const float m2 = mx * mx + my * my + mz * mz;
+                        if (m2 > dmax * dmax) continue;
+                        lvl = PCR_SHELL_LEVELS - 1;
+                        for (int l = PCR_SHELL_LEVELS - 2; l >= 1; --l) if (m2 <= (frac[l] * G.h) * (frac[l] * G.h)) lvl = l;
+                    }
+                    float w;
+                    memcpy(&w, &p, 4);
+                    lv[lvl].push_back(make_float4(t.x, t.y, t.z, w));
+                }
             }
+            const uint32_t base = (uint32_t)g->shell_pts.size();
+            g->shell_start.push_back(base);
+            uint32_t total = 0;
+            for (int l = 0; l < PCR_SHELL_LEVELS; ++l) {
+                for (size_t k = 0; k < lv[l].size(); ++k) {
+                    if ((total & 3u) == 0u) {
+                        const float lb = l >= 1 ? fmaxf(frac[l - 1] * G.h - slack_w, 0.0f) : 0.0f;
+                        g->shell_margin2.push_back(lb * lb);
+                    }
+                    g->shell_pts.push_back(lv[l][k]);
+                    ++total;
+                }
+            }
+            while (total & 3u) { g->shell_pts.push_back(make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f)); ++total; }
             ++ord;
         }
     }
-    g->nbr_start.push_back((uint32_t)g->nbr_entries.size());
-    g->nbr.bricks = g->nbr_bricks.data(); g->nbr.nstart = g->nbr_start.data(); g->nbr.entries = g->nbr_entries.data();
-    return (int64_t)g->nbr_entries.size();
+    g->shell_start.push_back((uint32_t)g->shell_pts.size());
+    const int64_t n_entries = (int64_t)g->shell_pts.size();
+    for (int k = 0; k < 4; ++k) g->shell_pts.push_back(make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f));
+    g->shell_margin2.push_back(3.0e38f);
+    g->shell.bricks = g->shell_bricks.data(); g->shell.start = g->shell_start.data(); g->shell.pts = g->shell_pts.data();
+    g->shell.margin2 = g->shell_margin2.data();
+    const float cov = fmaxf(dmax - slack_w, 0.0f);
+    g->shell.covered2 = cov * cov;
+    return n_entries;
 }
 
-// 1-NN through the neighbour lists (general search when the cell has no list), as the kernel does.
+// 1-NN through the shell lists (general search when the cell has no list), as the kernel does.
 // used_list[i] = 1 when the list path answered.
-void hs_nbr_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, float* dist, uint8_t* used_list) {
+void hs_shell_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, float* dist, uint8_t* used_list) {
     HostGrid* g = (HostGrid*)gp;
     const GridView& G = g->v;
     const float md = (float)max_dist;
     for (int64_t i = 0; i < m; ++i) {
         float d2;
         int pos;
-        const bool ok = nbr_nn(G, g->nbr, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
+        const bool ok = shell_nn(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
         if (!ok) pos = grid_nn(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2);
         if (used_list) used_list[i] = ok ? 1 : 0;
         if (pos >= 0) {
@@ -191,6 +231,49 @@ void hs_nbr_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* id
             memcpy(&j, &G.pts[pos].w, 4);
             idx[i] = j; dist[i] = sqrtf(d2);
         } else { idx[i] = -1; dist[i] = INFINITY; }
+    }
+}
+
+// Development aid: per warp row of 32 consecutive queries, groups of four evaluated by the
+// shell-list loop: out[0] = sum over rows of the max over lanes (lock-step cost), out[1] = sum
+// over all queries, out[2] = queries that fell back to the general search after the list,
+// out[3] = queries without a list.
+void hs_shell_study(void* gp, const float* q, int64_t m, double max_dist, double* out) {
+    HostGrid* g = (HostGrid*)gp;
+    const GridView& G = g->v;
+    const ShellLists& S = g->shell;
+    const float md2 = (float)max_dist * (float)max_dist;
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (int64_t r = 0; r < m; r += 32) {
+        long long mx = 0;
+        for (int64_t i = r; i < std::min(m, r + 32); ++i) {
+            const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
+            const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
+            if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) { out[3] += 1; continue; }
+            const int cx = (int)gx, cy = (int)gy, cz = (int)gz;
+            const uint4 rec = S.bricks[((size_t)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2)];
+            const unsigned long long band = ((unsigned long long)rec.y << 32) | rec.x;
+            const int bit = brick_bit(cx, cy, cz);
+            if (!((band >> bit) & 1ull)) { out[3] += 1; continue; }
+            const uint32_t ord = rec.z + (uint32_t)popc64(band & ((1ull << bit) - 1ull));
+            float best = md2;
+            long long groups = 0;
+            uint32_t k = S.start[ord];
+            const uint32_t e = S.start[ord + 1];
+            for (; k < e; k += 4) {
+                if (S.margin2[k >> 2] >= best) break;
+                ++groups;
+                for (int u = 0; u < 4; ++u) {
+                    const float4 t = S.pts[k + u];
+                    const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz, d = ex * ex + ey * ey + ez * ez;
+                    if (d < best) best = d;
+                }
+            }
+            if (k >= e && !(best <= S.covered2)) out[2] += 1;
+            out[1] += (double)groups;
+            mx = std::max(mx, groups);
+        }
+        out[0] += (double)mx;
     }
 }
 

@@ -34,9 +34,9 @@ def hs():
     lib.hs_flat_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
     lib.hs_flat_warp_sim.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_int]
-    lib.hs_nbr_build.restype = C.c_int64
-    lib.hs_nbr_build.argtypes = [C.c_void_p]
-    lib.hs_nbr_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hs_shell_build.restype = C.c_int64
+    lib.hs_shell_build.argtypes = [C.c_void_p, C.c_double]
+    lib.hs_shell_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.hs_linearize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_gn_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -163,10 +163,11 @@ def test_flat_search_matches_nested(hs, ch, tau, threads):
         hs.hs_grid_free(g)
 
 
-def test_neighbour_lists_match_general_search(hs):
-    """nbr_nn (per-cell neighbour lists + early exit + continuation into the general search)
-    returns exactly what grid_search() returns, for every regime: on the surface, displaced by
-    about one cell, far away (no list), outside the grid, NaN, tight and huge max_dist."""
+@pytest.mark.parametrize("dmax_frac", [1.0, 0.5, 1.7])
+def test_shell_lists_match_general_search(hs, dmax_frac):
+    """shell_nn (margin-ordered per-cell lists, margin-bound termination, continuation into the
+    general search) returns exactly what grid_search() returns, for every regime: on the surface,
+    displaced by about one cell, far away (no list), outside the grid, NaN, tight and huge max_dist."""
     rng = np.random.default_rng(6)
     pts = ds.make_urban_slab(20000, seed=7)
     near = ds.perturb_scan(pts, seed=3)[:4001]
@@ -177,14 +178,14 @@ def test_neighbour_lists_match_general_search(hs):
     bad[::5, 1] = np.nan
     for h in (0.08, 0.3, 0.45, 1.5):
         g = hs.hs_grid_build(ptr(pts), len(pts), float(h))
-        assert hs.hs_nbr_build(g) > 0
+        assert hs.hs_shell_build(g, dmax_frac) >= len(pts)
         for q, md, expect_lists in ((near, 2.0, h >= 0.45), (near, 0.03, h >= 0.45), (off, 2.0, h >= 1.5), (far, 2.0, False), (far, 1e9, False),
                                     (box, 2.0, False), (bad, 2.0, h >= 0.45), (pts[:2000], 1e30, True)):
             q = np.ascontiguousarray(q)
             i0 = np.empty(len(q), np.int64); d0 = np.empty(len(q), np.float32)
             hs.hs_nn(g, ptr(q), len(q), float(md), ptr(i0), ptr(d0))
             i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32); used = np.zeros(len(q), np.uint8)
-            hs.hs_nbr_nn(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1), ptr(used))
+            hs.hs_shell_nn(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1), ptr(used))
             assert np.array_equal(d0, d1)
             assert np.array_equal(i0 < 0, i1 < 0) and (i0 == i1).mean() > 0.999
             if expect_lists:
