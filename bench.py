@@ -255,6 +255,7 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, light=False)
     handle = reg.upload_scan(scan_host if on_host else scan_local.contiguous(), sort=True)
     set_scan_s = time.perf_counter() - t0
     stats = ctx.index_stats(0 if wl["cls"] in ("ICP", "PlaneICP") else 1)
+    stats["lists"] = ctx.shell_list_stats() if wl["cls"] in ("ICP", "PlaneICP") else ctx.voxel_list_stats()
 
     # ---- dry run: iterate sequence of one align() --------------------------------------------
     T0 = np.eye(4)
@@ -409,7 +410,8 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, light=False)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_scan_point": wl["bytes_per_point"],
-                         "kernel": f"linearize_lane_kernel<{wl['cls']}> (fused transform + exact NN + residual/Jacobian + reduction + GN step)"},
+                         "kernel": f"linearize_lane_kernel<{wl['cls']}> (fused transform + exact correspondence (per-cell list stream, "
+                                   f"straggler queue) + residual/Jacobian + reduction + GN step)"},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches),

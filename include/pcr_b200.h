@@ -98,11 +98,12 @@ int pcr_get_voxels(pcr_ctx* ctx, double* mean, double* cov, double* norm, double
 
 /* ---- scan side ------------------------------------------------------------------------- */
 
-/* Upload the scan once per align().  sort > 0 re-orders it along a Morton curve on the device,
- * which enables the tile-cooperative correspondence search (groups of consecutive scan points
- * share one candidate list); sort == 0 keeps the caller's order and uses the independent
- * per-point search; sort < 0 keeps the order but the caller promises it is spatially coherent.
- * Results are identical up to float64 summation order.  Replaces
+/* Upload the scan once per align().  sort > 0 re-orders it along a Morton curve on the device, so
+ * that the lanes of a warp query neighbouring cells (they then stream the same candidate lists);
+ * sort == 0 keeps the caller's order; sort < 0 keeps the order, the caller promises it is
+ * spatially coherent.  Results are identical up to float64 summation order.  With a host source
+ * the call returns once the caller's buffer has been read (the re-layout continues on the
+ * context's stream, every later call is ordered behind it).  Replaces
  * `source.astype(np.float32)` (registration.py:83). */
 int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort);
 
@@ -148,6 +149,12 @@ int pcr_voxel_query(pcr_ctx* ctx, const float* queries, int64_t m, int64_t* vidx
 int pcr_voxel_filter(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size,
                      float* out, int64_t* n_out);
 
+/* Voxel membership of every point (voxel.py:183-206, color_by_voxel's np.unique(..., return_inverse)):
+ * labels[i] = ordinal of point i's voxel (library order), coords[3 v .. 3 v + 2] = integer
+ * coordinate floor(p / voxel_size) of voxel v (room for n voxels), n_voxels = their number. */
+int pcr_voxel_labels(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size,
+                     int64_t* labels, int32_t* coords, int64_t* n_voxels);
+
 /* ---- multi-GPU (scan tile-sharded, target replicated) ----------- */
 
 /* 128-byte NCCL unique id, created on rank 0 and shipped to the other ranks by the caller. */
@@ -168,16 +175,6 @@ int pcr_stream(pcr_ctx* ctx, void** stream);
 /* Enqueue `reps` linearisations back to back WITHOUT host synchronisation (benchmark aid:
  * lets the caller bracket them with its own CUDA events on pcr_stream). */
 int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max_dist, int reps);
-/* Correspondence-search variant: 0 (default) = independent per-point search, 32 =
- * warp-cooperative search for sorted scans (kept for A/B measurements; slower on the measured
- * workloads, see profiles/).  Also settable at context creation through PCR_TILE_LANES. */
-int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes);
-/* Correspondence-search scheduling of the per-point search: mode 0 = every lane runs its query to
- * completion (nested loops), mode 1 = persistent-lane "flat" search (a lane that finishes a query
- * starts its next one at once; rounds of find-cell / evaluate <= ch candidates; cells are looked
- * for once >= tau lanes of the warp are out of work).  Same exact result either way.  ch <= 0 /
- * tau <= 0 keep the current values.  Also settable through PCR_SEARCH / PCR_FLAT_CH / PCR_FLAT_TAU. */
-int pcr_set_search_mode(pcr_ctx* ctx, int mode, int ch, int tau);
 /* Voxel-mean correspondences are read from exact per-cell candidate lists built with the voxels
  * (default on); 0 falls back to the general grid search everywhere (A/B and test hook). */
 int pcr_set_voxel_lists(pcr_ctx* ctx, int enable);
@@ -189,11 +186,6 @@ int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
  * PCR_SHELL_LISTS=0 / PCR_SHELL_DMAX / PCR_SHELL_MAX_GIB tune the build. */
 int pcr_set_shell_lists(pcr_ctx* ctx, int enable);
 int pcr_shell_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries, double* margin_cells);
-/* Test hook: exact NN of every resident scan point (storage order; upload with sort <= 0 to keep
- * the caller's order) under transform T through the TILE-COOPERATIVE search, against the target
- * points (which = 0) or the kept voxel means (which = 1); r0 = first search radius in cells.
- * idx = caller index of the match or -1, dist = Euclidean distance or inf. */
-int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_dist, double r0, int64_t* idx, float* dist);
 /* Test hook: correspondences parked by the LAST linearisation (any search variant): per resident
  * scan point, in storage order (upload with sort <= 0 to keep the caller's order), the caller
  * index of the matched target point (which = 0) / kept voxel (which = 1) or -1. */

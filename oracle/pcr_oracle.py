@@ -255,6 +255,21 @@ def voxel_filter(points, voxel_size):
     return np.stack(cols, axis=1).astype(np.float32)
 
 
+def color_by_voxel(points, voxel_size):
+    """Packed RGB per point, one seeded random colour per voxel in ascending key order
+    (voxel.py:183-206)."""
+    keys = voxel_keys(points, voxel_size)
+    uniq, inv = np.unique(keys, return_inverse=True)
+    inv = inv.ravel()
+    state = np.random.get_state()
+    np.random.seed(42)
+    colors = np.random.randint(0, 256, size=(len(uniq), 3), dtype=np.uint8)
+    np.random.set_state(state)
+    pc = colors[inv]
+    rgb = pc[:, 0].astype(np.uint32) << 16 | pc[:, 1].astype(np.uint32) << 8 | pc[:, 2].astype(np.uint32)
+    return np.rec.fromarrays([np.asarray(points).astype(np.float32), rgb], dtype=[('xyz', '<f4', (3,)), ('irgb', '<u4')])
+
+
 # --------------------------------------------------------------------------------------
 # kNN normals                                              estimate_normals.py:27-87
 # --------------------------------------------------------------------------------------

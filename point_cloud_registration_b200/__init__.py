@@ -12,10 +12,10 @@ from .plane_icp import PlaneICP
 from .icp import ICP
 from .ndt import NDT
 from .kdtree import KDTree
-from .voxel import VoxelGrid, voxel_filter, get_keys
+from .voxel import VoxelGrid, voxel_filter, color_by_voxel, get_keys
 from .estimate_normals import estimate_normals, get_norm_lines, estimate_norm_with_tree
 
 __all__ = ["Registration", "UploadedScan", "ICP", "PlaneICP", "VPlaneICP", "NDT", "KDTree", "VoxelGrid",
-           "voxel_filter", "get_keys", "estimate_normals", "estimate_norm_with_tree", "get_norm_lines",
+           "voxel_filter", "color_by_voxel", "get_keys", "estimate_normals", "estimate_norm_with_tree", "get_norm_lines",
            "makeRt", "makeT", "expSO3", "plus", "skew", "skews", "skew2", "skew_time_vector",
            "transform_points", "huber_weight"]

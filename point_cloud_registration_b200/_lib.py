@@ -46,6 +46,7 @@ SYMBOLS = {
     "pcr_knn": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
     "pcr_voxel_query": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "pcr_voxel_filter": (_i, [_vp, _vp, _i64, _i, _d, _vp, _pi64]),
+    "pcr_voxel_labels": (_i, [_vp, _vp, _i64, _i, _d, _vp, _vp, _pi64]),
     "pcr_comm_unique_id": (_i, [_vp]),
     "pcr_comm_init_rank": (_i, [_vp, _i, _i, _vp]),
     "pcr_comm_destroy": (_i, [_vp]),
@@ -53,14 +54,11 @@ SYMBOLS = {
     "pcr_launch_count": (_i, [_vp, _pi64]),
     "pcr_stream": (_i, [_vp, C.POINTER(_vp)]),
     "pcr_linearize_async": (_i, [_vp, _i, _vp, _d, _i]),
-    "pcr_set_tile_lanes": (_i, [_vp, _i]),
-    "pcr_set_search_mode": (_i, [_vp, _i, _i, _i]),
     "pcr_set_shell_lists": (_i, [_vp, _i]),
     "pcr_shell_list_stats": (_i, [_vp, _vp, _vp, _vp]),
     "pcr_debug_matches": (_i, [_vp, _i, _vp]),
     "pcr_set_voxel_lists": (_i, [_vp, _i]),
     "pcr_voxel_list_stats": (_i, [_vp, _pi64, _pi64]),
-    "pcr_debug_tile_nn": (_i, [_vp, _i, _vp, _d, _d, _vp, _vp]),
     "pcr_index_stats": (_i, [_vp, _i, C.POINTER(_d), _pi64, _pi64, _pi64]),
 }
 
@@ -238,7 +236,7 @@ class Context:
     # -- scan side ------------------------------------------------------------------------
     def set_scan(self, pts_f32, sort=True):
         """sort: True/1 Morton-sort on the device; False/0 keep order (per-point search);
-        -1 keep order, caller promises spatial coherence (tile-cooperative search)."""
+        -1 keep order, caller promises spatial coherence."""
         self._check(self._lib.pcr_set_scan(self._h, _ptr(pts_f32), pts_f32.shape[0], int(sort)))
 
     def set_voxel_lists(self, enable):
@@ -249,9 +247,6 @@ class Context:
         self._check(self._lib.pcr_voxel_list_stats(self._h, C.byref(a), C.byref(b)))
         return dict(band_cells=a.value, entries=b.value)
 
-    def set_tile_lanes(self, lanes):
-        self._check(self._lib.pcr_set_tile_lanes(self._h, int(lanes)))
-
     def set_shell_lists(self, enable):
         self._check(self._lib.pcr_set_shell_lists(self._h, int(bool(enable))))
 
@@ -260,22 +255,11 @@ class Context:
         self._check(self._lib.pcr_shell_list_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
         return dict(band_cells=a.value, entries=b.value, margin_cells=m.value, bytes=b.value * 17)
 
-    def set_search_mode(self, mode, ch=0, tau=0):
-        """mode 0: nested per-lane search, 1: persistent-lane flat search (see pcr_b200.h)."""
-        self._check(self._lib.pcr_set_search_mode(self._h, int(mode), int(ch), int(tau)))
-
     def debug_matches(self, n_scan, which=0):
         """Caller indices matched by the last linearisation, per resident scan point (storage order)."""
         idx = np.empty(n_scan, dtype=np.int64)
         self._check(self._lib.pcr_debug_matches(self._h, int(which), _ptr(idx)))
         return idx
-
-    def debug_tile_nn(self, n_scan, T, max_dist, r0=0.5, which=0):
-        T = np.ascontiguousarray(T, dtype=np.float64)
-        idx = np.empty(n_scan, dtype=np.int64)
-        dist = np.empty(n_scan, dtype=np.float32)
-        self._check(self._lib.pcr_debug_tile_nn(self._h, int(which), _ptr(T), float(max_dist), float(r0), _ptr(idx), _ptr(dist)))
-        return dist, idx
 
     def linearize(self, method, T, max_dist):
         T = np.ascontiguousarray(T, dtype=np.float64)
@@ -332,6 +316,16 @@ class Context:
         self._check(self._lib.pcr_voxel_filter(self._h, _ptr(arr), arr.shape[0], is64, float(voxel_size), _ptr(out),
                                                C.byref(n_out)))
         return out[:n_out.value].copy()
+
+    def voxel_labels(self, pts, voxel_size):
+        """(labels (N,) int64, voxel coordinates (V,3) int32): voxel membership of every point."""
+        arr, is64 = self._f32_or_f64(pts)
+        labels = np.empty(arr.shape[0], dtype=np.int64)
+        coords = np.empty((arr.shape[0], 3), dtype=np.int32)
+        nv = C.c_int64(0)
+        self._check(self._lib.pcr_voxel_labels(self._h, _ptr(arr), arr.shape[0], is64, float(voxel_size), _ptr(labels), _ptr(coords),
+                                               C.byref(nv)))
+        return labels, coords[:nv.value].copy()
 
     # -- multi GPU ------------------------------------------------------------------------
     @staticmethod

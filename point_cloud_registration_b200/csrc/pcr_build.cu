@@ -1029,6 +1029,40 @@ static int voxel_filter_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     return PCR_OK;
 }
 
+// per point (caller order): ordinal of its voxel; per voxel: its integer coordinate floor(p / size)
+__global__ void voxel_label_kernel(const uint32_t* __restrict__ vals, const uint32_t* __restrict__ flags, const uint32_t* __restrict__ ords,
+                                   const int* __restrict__ coords, long long n, long long* __restrict__ labels, int* __restrict__ gcoords) {
+    const long long s = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    const uint32_t j = vals[s], grp = ords[s] + flags[s] - 1u;
+    labels[j] = (long long)grp;
+    if (flags[s]) { gcoords[3 * (size_t)grp] = coords[3 * (size_t)j]; gcoords[3 * (size_t)grp + 1] = coords[3 * (size_t)j + 1]; gcoords[3 * (size_t)grp + 2] = coords[3 * (size_t)j + 2]; }
+}
+
+template <typename T>
+static int voxel_labels_impl(pcr_ctx* ctx, const void* xyz, long long n, double voxel_size, long long* labels, int* gcoords, long long* n_groups) {
+    VoxelFront F;
+    int rc = voxel_front<T>(ctx, xyz, n, voxel_size, 0, F);
+    if (rc) { F.release(); return rc; }
+    // buffers left behind by voxel_front: sorted original indices, head flags, head ordinals, coordinates
+    const uint32_t* v_out = ctx->tmp_c.as<uint32_t>() + n;
+    const uint32_t* flags = ctx->tmp_d.as<uint32_t>();
+    const uint32_t* ords = flags + n;
+    const int* coords = ctx->tmp_e.as<int>() + 16;
+    DevBuf d_lab, d_gc;
+    PCR_CUDA(d_lab.ensure((size_t)n * 8));
+    PCR_CUDA(d_gc.ensure((size_t)F.n_seg * 12));
+    voxel_label_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(v_out, flags, ords, coords, n, d_lab.as<long long>(), d_gc.as<int>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(cudaMemcpyAsync(labels, d_lab.p, (size_t)n * 8, is_device_pointer(labels) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaMemcpyAsync(gcoords, d_gc.p, (size_t)F.n_seg * 12, is_device_pointer(gcoords) ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_groups = F.n_seg;
+    d_lab.release(); d_gc.release();
+    F.release();
+    return PCR_OK;
+}
+
 }  // namespace pcr
 
 using namespace pcr;
@@ -1073,23 +1107,14 @@ int pcr_create(int device_id, pcr_ctx** out) {
         delete ctx;
         return fail(nullptr, PCR_ERR_CUDA, m);
     }
-    if (const char* e = getenv("PCR_TILE_LANES")) {
-        const int g = atoi(e);
-        ctx->tile_lanes = g == 32 ? 32 : 0;
-    }
-    if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 3;
+    if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) >= 3 && atoi(e) <= 6 ? atoi(e) : 4;
     if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 24.0;
-    if (const char* e = getenv("PCR_R0_MIN")) ctx->r0_min = (float)atof(e);
-    if (const char* e = getenv("PCR_WARM")) ctx->warm_start = atoi(e);
-    if (const char* e = getenv("PCR_LOCAL_R1")) ctx->local_r1 = (float)atof(e);
     if (const char* e = getenv("PCR_SHELL_DMAX")) ctx->shell_dmax_frac = atof(e) > 0.0 && atof(e) <= 2.0 ? atof(e) : 1.0;
     if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 24.0;
     if (const char* e = getenv("PCR_QUEUE")) ctx->use_queue = atoi(e) != 0;
     if (const char* e = getenv("PCR_LIST_DILATE")) ctx->list_dilate = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 2;
     if (const char* e = getenv("PCR_LIST_RADIUS")) ctx->list_radius = atoi(e) >= 2 && atoi(e) <= 6 ? atoi(e) : 3;
-    if (const char* e = getenv("PCR_SEARCH")) ctx->search_mode = (!strcmp(e, "flat") || atoi(e) == 1) ? 1 : 0;
-    if (const char* e = getenv("PCR_FLAT_CH")) ctx->flat_ch = atoi(e) >= 4 ? atoi(e) : 32;
-    if (const char* e = getenv("PCR_FLAT_TAU")) ctx->flat_tau = atoi(e) >= 1 && atoi(e) <= 32 ? atoi(e) : 1;
+    if (const char* e = getenv("PCR_SPLIT")) ctx->split_passes = atoi(e) != 0;
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
     *out = ctx;
@@ -1289,6 +1314,17 @@ int pcr_voxel_filter(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, doubl
     long long no = 0;
     int rc = is_f64 ? voxel_filter_impl<double>(ctx, xyz, n, voxel_size, out, &no) : voxel_filter_impl<float>(ctx, xyz, n, voxel_size, out, &no);
     *n_out = no;
+    return rc;
+}
+
+int pcr_voxel_labels(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size, int64_t* labels, int32_t* coords, int64_t* n_voxels) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!xyz || !labels || !coords || !n_voxels || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_voxel_labels: bad arguments");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    long long ng = 0;
+    int rc = is_f64 ? voxel_labels_impl<double>(ctx, xyz, n, voxel_size, (long long*)labels, coords, &ng)
+                    : voxel_labels_impl<float>(ctx, xyz, n, voxel_size, (long long*)labels, coords, &ng);
+    *n_voxels = ng;
     return rc;
 }
 

@@ -26,7 +26,7 @@ struct LoopState {
     int iter;               // linearisations executed so far
     int done;               // 0 running, 1 converged, 2 singular H
     unsigned int ticket;    // block arrival counter of the running linearise kernel
-    float search_r0;        // first search radius (grid cells) suggested for the next linearisation
+    float reserved;
 };
 
 struct DevBuf {
@@ -98,17 +98,11 @@ struct pcr_ctx {
     long long n_scan = 0;         // real points
     long long n_scan_pad = 0;     // padded to a multiple of 32 with NaN (whole tiles enter the kernel loop)
     bool scan_set = false;
-    bool scan_sorted = false;     // spatially coherent order -> tile-cooperative search
-    int tile_lanes = 0;           // 0: per-point search (default, fastest measured); 32: warp-cooperative search for sorted scans
+    bool scan_sorted = false;     // spatially coherent order (Morton-sorted on upload, or promised by the caller)
     double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
-    float r0_min = 0.0f;          // lower bound of the first cooperative search radius (cells)
-    int warm_start = 0;           // per-point kernel: warm-start the search from the previous matches (measured: no gain)
-    int min_blocks = 3;           // __launch_bounds__ min blocks/SM variant of the linearise kernels (2, 3 or 4)
-    float local_r1 = 1.0f;        // tile kernel: warm-start radius (cells) handled by the per-lane local search
-    int search_mode = 0;          // 0: nested per-lane search (variant B), 1: persistent-lane flat search (variant C)
-    int flat_ch = 32;             // flat search: candidates per lane and round
-    int flat_tau = 1;             // flat search: lanes out of work before phase A runs
-    int lin_blocks_per_sm[4][8] = {};   // cached occupancy per (method, variant)
+    int min_blocks = 4;           // resident blocks per SM requested for the correspondence pass (3..6)
+    int split_passes = 1;         // 1: correspond + accumulate kernels, 0: one fused kernel (A/B)
+    int lin_blocks_per_sm[4][9] = {};   // cached occupancy per (method, kernel variant)
     pcr::DevBuf scan_x, scan_y, scan_z;
     pcr::DevBuf scan_prev;        // int[n_pad]: position matched by the previous linearisation (warm start)
     int prev_which = -1;          // index the positions refer to (0 target grid, 1 voxel grid, -1 none)

@@ -259,20 +259,28 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
     const uint32_t s = S.start[ord], e = S.start[ord + 1];
     float best = max_d2;
     float best_w = 0.0f;
-    bool have = false;
+    bool have = false, exhausted = true;
+    // software pipeline: the next group of four (and its margin bound) is in flight while the
+    // current one is evaluated; reading one group past the end is safe (the next list or the
+    // sentinels that terminate the array) and its values are never used
     uint32_t k = s;
-    for (; k < e; k += 4) {
-        if (S.margin2[k >> 2] >= best) break;                 // everything from here on is at least this far
-        const float4 t0 = S.pts[k], t1 = S.pts[k + 1], t2 = S.pts[k + 2], t3 = S.pts[k + 3];
+    float m = S.margin2[k >> 2];
+    float4 t0 = S.pts[k], t1 = S.pts[k + 1], t2 = S.pts[k + 2], t3 = S.pts[k + 3];
+    while (k < e) {
+        if (m >= best) { exhausted = false; break; }          // everything from here on is at least this far
+        const float4 c0 = t0, c1 = t1, c2 = t2, c3 = t3;
+        k += 4;
+        m = S.margin2[k >> 2];
+        t0 = S.pts[k]; t1 = S.pts[k + 1]; t2 = S.pts[k + 2]; t3 = S.pts[k + 3];
         float ex, ey, ez, d;
-        ex = t0.x - qx; ey = t0.y - qy; ez = t0.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = t0.w; have = true; }
-        ex = t1.x - qx; ey = t1.y - qy; ez = t1.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = t1.w; have = true; }
-        ex = t2.x - qx; ey = t2.y - qy; ez = t2.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = t2.w; have = true; }
-        ex = t3.x - qx; ey = t3.y - qy; ez = t3.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = t3.w; have = true; }
+        ex = c0.x - qx; ey = c0.y - qy; ez = c0.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = c0.w; have = true; }
+        ex = c1.x - qx; ey = c1.y - qy; ez = c1.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = c1.w; have = true; }
+        ex = c2.x - qx; ey = c2.y - qy; ez = c2.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = c2.w; have = true; }
+        ex = c3.x - qx; ey = c3.y - qy; ez = c3.z - qz; d = ex * ex + ey * ey + ez * ez;
+        if (d < best) { best = d; best_w = c3.w; have = true; }
     }
     out_d2 = best;
 #if defined(__CUDA_ARCH__)
@@ -282,7 +290,7 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
 #endif
     // stopped by a margin bound: final.  List exhausted: final only if the best (or, with no
     // candidate, the search radius) lies within the covered margin.
-    return (k >= e && !(best <= S.covered2)) ? 2 : 1;
+    return (exhausted && !(best <= S.covered2)) ? 2 : 1;
 }
 
 // 1-NN through the shell lists with the general search as continuation (host replay, and the

@@ -1,26 +1,29 @@
-// The per-iteration hot path of libpcr_b200.so (sm_100a): ONE fused kernel per Gauss-Newton
-// linearisation
+// The per-iteration hot path of libpcr_b200.so (sm_100a).  One Gauss-Newton linearisation =
 //
-//   coalesced float4 loads of the SoA scan -> SE(3) transform (float32) -> exact
-//   correspondence search in the brick grid -> residual + 6-DoF Jacobian terms ->
-//   per-thread float32 partial sums -> float64 warp-shuffle + shared-memory block reduction
-//   -> per-block partial record -> the LAST block to arrive sums the partials in a fixed
-//   order (deterministic), assembles the 29-entry record and (on-device loop) performs the
-//   6x6 solve, the stop test and the SE(3) update.
+//   correspond   coalesced loads of the SoA scan -> SE(3) transform (float32) -> exact nearest
+//                neighbour: every query streams the list of its cell (voxel means: exact candidate
+//                list; target points: margin-ordered shell list); the few queries a list cannot
+//                settle go to a block queue and are searched in the brick grid with all lanes
+//                busy -> matched position parked per scan slot (4 B/point)
+//   accumulate   gather the matched record -> residual + 6-DoF Jacobian terms -> per-thread float32
+//                sums -> float64 warp shuffles + shared-memory block reduction -> per-block partial
+//                -> the LAST block to arrive sums the partials in a fixed order (deterministic),
+//                assembles the 29-entry record and (on-device loop) performs the 6x6 solve, the stop
+//                test and the SE(3) update.
 //
+// The two passes run as two kernels (default: the latency-bound list streaming wants many resident
+// warps, the 30-accumulator reduction wants registers) or fused in one (PCR_SPLIT=0, A/B).
 // Replaces calc_H_g_e2 of icp.py:24-57, plane_icp.py:30-69, voxelized_plane_icp.py:23-64,
 // ndt.py:24-57 and the loop of registration.py:89-111.  No tensor cores: the path is a
-// gather + 29-term reduction (arithmetic intensity ~3 flop/B), bounded by HBM / L2 traffic.
+// gather + 29-term reduction (arithmetic intensity ~3 flop/B).
 #include <dlfcn.h>
 
 #include <cub/cub.cuh>
 
 #include "pcr_context.cuh"
 #include "pcr_grid.cuh"
-#include "pcr_flat_search.cuh"
 #include "pcr_linalg.cuh"
 #include "pcr_terms.cuh"
-#include "pcr_tile_search.cuh"
 
 namespace pcr {
 
@@ -37,12 +40,6 @@ struct LinParams {
     int use_queue;                                       // park list misses in the block queue (pass 1b) instead of searching in place
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
-    float local_r1;           // tile kernel: warm-start radius (cells) up to which the per-lane local search is used
-    float r0_min;             // lower bound of the first cooperative search radius (cells)
-    int warm;                 // per-point kernel: use P.prev as warm start
-    int flat_ch;              // flat kernel: candidates evaluated per lane and round
-    int flat_tau;             // flat kernel: lanes that must be out of work before the warp looks for new cells
-    float r0_param;           // first search radius (grid units) when use_param_T; <= 0: take st->search_r0
     double T_param[16];
     int use_param_T;          // 1: transform comes from T_param, 0: from st->T (device loop)
     int device_loop;          // 1: last block performs the Gauss-Newton step on st
@@ -53,8 +50,7 @@ struct LinParams {
     double* out_mapped;       // pinned host memory (may be NULL): rec[32], T[16], iter, done
 };
 
-// accumulators per thread: the method's sums + one extra (sum of NN distances, feeds the
-// first-radius heuristic of the next iteration)
+// accumulators per thread
 template <int METHOD> struct NAcc { static constexpr int value = PCR_NEQ; };
 template <> struct NAcc<PCR_METHOD_ICP> { static constexpr int value = 17; };
 
@@ -97,10 +93,6 @@ __device__ __noinline__ void finish_iteration(const LinParams& P, BlockShared& s
         for (int i = 0; i < PCR_NEQ; ++i) rec[i] = sh.sum[i];
     }
     for (int i = 0; i < PCR_NEQ; ++i) st->rec[i] = rec[i];
-    // first search radius of the next linearisation: 1.25 x mean NN distance, in grid cells
-    const double sum_d = sh.sum[NAcc<METHOD>::value];
-    const double mean_d = rec[28] > 0.0 ? sum_d / rec[28] : 0.0;
-    st->search_r0 = (float)fmin(fmax(1.25 * mean_d * (double)P.grid.inv_h, 0.05), 4.0);
     st->ticket = 0u;
     int iter = st->iter;
     int done = 0;
@@ -135,7 +127,7 @@ __device__ __noinline__ void finish_iteration(const LinParams& P, BlockShared& s
 // the last block to arrive reduces all partials in a fixed order and finishes the iteration.
 template <int METHOD>
 __device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShared& sh, const float* acc) {
-    constexpr int NRED = NAcc<METHOD>::value + 1;
+    constexpr int NRED = NAcc<METHOD>::value;
     constexpr int NWARP = kLinThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -172,95 +164,36 @@ __device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShare
     if (threadIdx.x == 0) finish_iteration<METHOD>(P, sh);
 }
 
-__device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, Pose32& pose, float& r0) {
+__device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, Pose32& pose) {
     LoopState* st = P.st;
     if (threadIdx.x == 0) sh.flag = P.use_param_T ? 0 : *((volatile int*)&st->done);   // device loop finished?
     if (threadIdx.x < 16) sh.T[threadIdx.x] = P.use_param_T ? P.T_param[threadIdx.x] : ((volatile double*)st->T)[threadIdx.x];
     __syncthreads();
     if (sh.flag) return false;
     pose32_from_T(sh.T, pose);
-    r0 = P.r0_param > 0.f ? P.r0_param : *((volatile float*)&st->search_r0);
-    if (!(r0 > 0.f)) r0 = 0.5f;
-    if (P.r0_min > r0) r0 = P.r0_min;
     return true;
 }
 
-// ---- variant A: tile-cooperative search (sorted scans) -----------------------------------------
-template <int METHOD, int G, int MINB>
-__global__ void __launch_bounds__(kLinThreads, MINB) linearize_tile_kernel(const LinParams P) {
-    constexpr int NACC = NAcc<METHOD>::value;
-    __shared__ BlockShared sh;
-    __shared__ TileScratch<G> scratch[kLinThreads / G];
-    Pose32 pose;
-    float r0;
-    if (!load_pose(P, sh, pose, r0)) return;                // loop already finished: nothing to do
-
-    float acc[NACC + 1];
-#pragma unroll
-    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
-
-    const cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
-    TileScratch<G>& S = scratch[threadIdx.x / G];
-    const long long stride = (long long)gridDim.x * kLinThreads;
-    for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride) {
-        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);   // coalesced, NaN = padding
-        float qx, qy, qz;
-        transform32(pose, px, py, pz, qx, qy, qz);
-        // warm start: last iteration's match bounds this iteration's search radius
-        float d2 = P.max_d2;
-        int pos = __ldg(P.prev + i);
-        if (pos >= 0) {
-            const float4 t = __ldg(P.grid.pts + pos);
-            const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-            const float dw = ex * ex + ey * ey + ez * ez;
-            if (dw < P.max_d2) d2 = dw; else pos = -1;
-        }
-        // a tight warm-start bound (radius <= local_r1 cells) is settled by the per-lane local
-        // search; everything else (first iteration, large moves, outliers) searches cooperatively
-        bool need = px == px;
-        if (pos >= 0) {
-            const float r = sqrtf(d2) * P.grid.inv_h * 1.000001f + P.grid.slack;
-            if (r <= P.local_r1) {
-                const float gx = (qx - P.grid.ox) * P.grid.inv_h, gy = (qy - P.grid.oy) * P.grid.inv_h, gz = (qz - P.grid.oz) * P.grid.inv_h;
-                local_nn_search(P.grid, qx, qy, qz, gx, gy, gz, r, d2, pos);
-                need = false;
-            }
-        }
-        if (tile.any(need)) tile_nn_search<G>(tile, P.grid, S, need, qx, qy, qz, r0, P.max_d2, d2, pos);
-        P.prev[i] = pos;
-        if (pos >= 0) {
-            accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
-            acc[NACC] += sqrtf(d2);
-        }
-    }
-    reduce_and_finish<METHOD>(P, sh, acc);
+// The general brick-grid search as an out-of-line call: it only serves stragglers, and inlined it
+// would set the register budget (and so the occupancy) of the list-streaming loop around it.
+__device__ __noinline__ int general_nn(const GridView& G, float qx, float qy, float qz, float max_d2) {
+    float d2;
+    return grid_nn(G, qx, qy, qz, max_d2, d2);
 }
 
-// ---- variant B: independent per-lane search (any scan order) -----------------------------------
-// Two passes over the thread's own points keep the register footprint at max(search,
-// accumulate) instead of their sum: pass 1 searches and parks the matched position in P.prev
-// (4 B/point, L2-resident), pass 2 re-reads it, gathers the record and accumulates.
-template <int METHOD, int MINB>
-__global__ void __launch_bounds__(kLinThreads, MINB) linearize_lane_kernel(const LinParams P) {
-    constexpr int NACC = NAcc<METHOD>::value;
+// ---- pass 1: correspondences ---------------------------------------------------------------------
+// 1a: every query streams the list of its cell -- lanes of one cell read the same addresses for
+// nearly the same number of steps.  The few queries a list cannot settle (no list for the cell,
+// or the best still beyond the listed margin) are NOT searched here, where they would stall the
+// other 31 lanes of their warp: their scan slots go to a block queue.  1b: the block works the
+// queue off with every lane busy (general brick-grid search).
+template <int METHOD>
+__device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32& pose, int* sq, int* sq_len) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
-    __shared__ BlockShared sh;
-    __shared__ int sq[kQueueCap];                        // scan slots whose correspondence needs the general search
-    __shared__ int sq_len;
-    Pose32 pose;
-    float r0;
-    if (threadIdx.x == 0) sq_len = 0;
-    if (!load_pose(P, sh, pose, r0)) return;
     const long long stride = (long long)gridDim.x * kLinThreads;
     const long long first = blockIdx.x * (long long)kLinThreads + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const bool lists = kVoxel ? (P.use_lists != 0) : (P.use_shell != 0);
-
-    // Pass 1a: every query streams the list of its cell (voxel means: exact candidate list; target
-    // points: margin-ordered shell list) -- lanes of one cell read the same addresses for nearly the
-    // same number of steps.  The few queries a list cannot settle (no list for the cell, or the
-    // best still beyond the listed margin) are NOT searched here, where they would stall the other
-    // 31 lanes of their warp: their slots go to a block queue ...
     for (long long i = first; i < P.n_pad; i += stride) {       // n_pad and stride are multiples of 32: warps stay whole
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
@@ -278,148 +211,85 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_lane_kernel(const
                 if (m) {
                     const int leader = __ffs(m) - 1;
                     int base = 0;
-                    if (lane == leader) base = atomicAdd(&sq_len, __popc(m));
+                    if (lane == leader) base = atomicAdd(sq_len, __popc(m));
                     base = __shfl_sync(0xffffffffu, base, leader);
                     if (pending) {
                         const int slot = base + __popc(m & ((1u << lane) - 1u));
                         if (slot < kQueueCap) sq[slot] = (int)i;
-                        else pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);     // queue full: search in place
+                        else pos = general_nn(P.grid, qx, qy, qz, P.max_d2);       // queue full: search in place
                     }
                 }
             } else if (pending) {
-                pos = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
+                pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
             }
-        } else {
-            pos = grid_nn_warm(P.grid, qx, qy, qz, P.max_d2, P.warm ? P.prev[i] : -1, d2);
+        } else if (px == px) {
+            pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
         }
         P.prev[i] = pos;
     }
-    // ... Pass 1b: and the block works the queue off with every lane busy.
     __syncthreads();
-    {
-        const int nq = sq_len < kQueueCap ? sq_len : kQueueCap;
-        for (int k = threadIdx.x; k < nq; k += kLinThreads) {
-            const long long i = sq[k];
-            const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
-            float qx, qy, qz, d2;
-            transform32(pose, px, py, pz, qx, qy, qz);
-            P.prev[i] = grid_nn(P.grid, qx, qy, qz, P.max_d2, d2);
-        }
-    }
-    __syncthreads();                                             // queue results were parked by other threads of this block
-
-    float acc[NACC + 1];
-#pragma unroll
-    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
-    for (long long i = first; i < P.n_pad; i += stride) {
-        const int pos = P.prev[i];                       // written by this very thread in pass 1
-        if (pos < 0) continue;
+    const int nq = *sq_len < kQueueCap ? *sq_len : kQueueCap;
+    for (int k = threadIdx.x; k < nq; k += kLinThreads) {
+        const long long i = sq[k];
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
-        accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
-        const float4 t = __ldg(P.grid.pts + pos);
-        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-        acc[NACC] += sqrtf(ex * ex + ey * ey + ez * ez);
+        P.prev[i] = general_nn(P.grid, qx, qy, qz, P.max_d2);
     }
-    reduce_and_finish<METHOD>(P, sh, acc);
 }
 
-
-// ---- variant C: persistent-lane ("flat") search ---------------------------------------------------
-// Pass 1 is ONE warp loop of rounds { phase A: lanes without candidates find their next cell,
-// plan their next pass, or -- when their query is finished -- park the result and start their
-// next query | phase B: every lane evaluates <= flat_ch candidates }.  A lane never waits for the
-// slowest query of its row (the nested search's loss, 10-13 active lanes per instruction), and
-// phase A only runs once >= flat_tau lanes are out of work, so it executes with many lanes
-// active.  Lane t still owns scan slots t, t + stride, ... : pass 2 (identical to variant B) reads
-// back exactly what the same thread parked, and the summation order stays fixed.
-template <int METHOD, int MINB>
-__global__ void __launch_bounds__(kLinThreads, MINB) linearize_flat_kernel(const LinParams P) {
+// ---- pass 2: residual + Jacobian terms of the parked correspondences, reduction, GN step ----------
+template <int METHOD>
+__device__ __forceinline__ void accumulate_pass(const LinParams& P, BlockShared& sh, const Pose32& pose) {
     constexpr int NACC = NAcc<METHOD>::value;
-    constexpr bool kLists = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
-    __shared__ BlockShared sh;
-    Pose32 pose;
-    float r0;
-    if (!load_pose(P, sh, pose, r0)) return;
     const long long stride = (long long)gridDim.x * kLinThreads;
     const long long first = blockIdx.x * (long long)kLinThreads + threadIdx.x;
-    {
-        FlatLane L;
-        L.p = L.e = 0u;
-        long long i = first;
-        bool active = false, lmode = false;
-        bool done = i >= P.n_pad;
-        const bool use_lists = kLists && P.use_lists;
-        const int ch = P.flat_ch, tau = P.flat_tau;
-        for (;;) {
-            const bool need = !done && L.p == L.e;
-            const unsigned needm = __ballot_sync(0xffffffffu, need);
-            const unsigned havem = __ballot_sync(0xffffffffu, !done && L.p != L.e);
-            if ((needm | havem) == 0u) break;
-            if (need && (__popc(needm) >= tau || havem == 0u)) {
-                while (L.p == L.e) {
-                    if (active) {
-                        if (!lmode) {
-                            if (flat_next_cell(P.grid, L)) break;
-                            if (flat_next_pass(P.grid, L)) continue;
-                        }
-                        P.prev[i] = L.best_pos;
-                        i += stride;
-                        active = false;
-                    }
-                    if (i >= P.n_pad) { done = true; break; }
-                    const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
-                    float qx, qy, qz;
-                    transform32(pose, px, py, pz, qx, qy, qz);
-                    if (use_lists && flat_begin_list(P.grid, P.lists, L, qx, qy, qz, P.max_d2)) { lmode = true; active = true; }
-                    else if (flat_begin(P.grid, L, qx, qy, qz, P.max_d2)) { lmode = false; active = true; }
-                    else { P.prev[i] = -1; i += stride; }
-                }
-            }
-            flat_eval(P.grid, L, ch, (kLists && lmode) ? P.lists.list_idx : nullptr);
-        }
-    }
-
-    float acc[NACC + 1];
+    float acc[NACC];
 #pragma unroll
-    for (int i = 0; i <= NACC; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
     for (long long i = first; i < P.n_pad; i += stride) {
-        const int pos = P.prev[i];                       // parked in pass 1 by this block
+        const int pos = P.prev[i];
         if (pos < 0) continue;
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
         transform32(pose, px, py, pz, qx, qy, qz);
         accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
-        const float4 t = __ldg(P.grid.pts + pos);
-        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-        acc[NACC] += sqrtf(ex * ex + ey * ey + ez * ez);
     }
     reduce_and_finish<METHOD>(P, sh, acc);
 }
 
-// Debug / test kernel: tile-cooperative NN of the resident scan under T_param -> per scan slot
-// (storage order) the matched position's payload index and the distance.
-template <int G>
-__global__ void __launch_bounds__(kLinThreads) tile_nn_debug_kernel(const LinParams P, long long* __restrict__ idx, float* __restrict__ dist) {
+// split form (default): two kernels, each with the occupancy it wants
+template <int METHOD, int MINB>
+__global__ void __launch_bounds__(kLinThreads, MINB) correspond_kernel(const LinParams P) {
     __shared__ BlockShared sh;
-    __shared__ TileScratch<G> scratch[kLinThreads / G];
+    __shared__ int sq[kQueueCap];
+    __shared__ int sq_len;
     Pose32 pose;
-    float r0;
-    if (!load_pose(P, sh, pose, r0)) return;
-    const cg::thread_block_tile<G> tile = cg::tiled_partition<G>(cg::this_thread_block());
-    TileScratch<G>& S = scratch[threadIdx.x / G];
-    const long long stride = (long long)gridDim.x * kLinThreads;
-    for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride) {
-        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
-        float qx, qy, qz;
-        transform32(pose, px, py, pz, qx, qy, qz);
-        float d2 = P.max_d2;
-        int pos = -1;
-        tile_nn_search<G>(tile, P.grid, S, px == px, qx, qy, qz, r0, P.max_d2, d2, pos);
-        idx[i] = pos >= 0 ? (long long)__float_as_uint(P.grid.pts[pos].w) : -1ll;
-        dist[i] = pos >= 0 ? sqrtf(d2) : __int_as_float(0x7f800000);
-    }
+    if (threadIdx.x == 0) sq_len = 0;
+    if (!load_pose(P, sh, pose)) return;                         // loop already finished: nothing to do
+    correspond_pass<METHOD>(P, pose, sq, &sq_len);
+}
+
+template <int METHOD>
+__global__ void __launch_bounds__(kLinThreads, 3) accumulate_kernel(const LinParams P) {
+    __shared__ BlockShared sh;
+    Pose32 pose;
+    if (!load_pose(P, sh, pose)) return;
+    accumulate_pass<METHOD>(P, sh, pose);
+}
+
+// fused form (PCR_SPLIT=0): both passes in one kernel; thread t accumulates the slots it searched
+template <int METHOD, int MINB>
+__global__ void __launch_bounds__(kLinThreads, MINB) linearize_fused_kernel(const LinParams P) {
+    __shared__ BlockShared sh;
+    __shared__ int sq[kQueueCap];
+    __shared__ int sq_len;
+    Pose32 pose;
+    if (threadIdx.x == 0) sq_len = 0;
+    if (!load_pose(P, sh, pose)) return;
+    correspond_pass<METHOD>(P, pose, sq, &sq_len);
+    __syncthreads();                                             // queue results were parked by other threads of this block
+    accumulate_pass<METHOD>(P, sh, pose);
 }
 
 __global__ void matches_kernel(const int* __restrict__ prev, const float4* __restrict__ pts, long long n, long long* __restrict__ idx) {
@@ -455,7 +325,7 @@ __global__ void gn_step_kernel(LoopState* st, double tol, int max_iter) {
 struct T16 { double v[16]; };
 __global__ void loop_init_kernel(LoopState* st, T16 T0) {
     if (threadIdx.x < 16) st->T[threadIdx.x] = T0.v[threadIdx.x];
-    if (threadIdx.x == 0) { st->iter = 0; st->done = 0; st->ticket = 0u; st->dx_norm = 0.0; st->search_r0 = 0.5f; }
+    if (threadIdx.x == 0) { st->iter = 0; st->done = 0; st->ticket = 0u; st->dx_norm = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -642,7 +512,6 @@ static int check_method(pcr_ctx* ctx, int method) {
 static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P) {
     P.sx = ctx->scan_x.as<float>(); P.sy = ctx->scan_y.as<float>(); P.sz = ctx->scan_z.as<float>();
     P.n_pad = ctx->n_scan_pad;
-    P.r0_param = 0.f;
     P.grid = (method == PCR_ICP || method == PCR_PLANE) ? ctx->tgt_grid.view : ctx->vox_grid.view;
     P.nrm = ctx->tgt_nrm_sorted.as<float4>();
     P.prev = ctx->scan_prev.as<int>();
@@ -651,11 +520,6 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.shell = ctx->tgt_shell;
     P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
     P.use_queue = ctx->use_queue;
-    P.local_r1 = ctx->local_r1;
-    P.warm = ctx->warm_start;
-    P.flat_ch = ctx->flat_ch;
-    P.flat_tau = ctx->flat_tau;
-    P.r0_min = ctx->r0_min;
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
     const float md = (float)max_dist;
     P.max_d2 = md * md;
@@ -664,39 +528,33 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.out_mapped = ctx->d_out_mapped;
 }
 
+template <typename K>
+static int blocks_for_kernel(pcr_ctx* ctx, K kernel, int& cached, long long n_pad) {
+    if (cached == 0) cached = blocks_per_sm(kernel);
+    return lin_grid_blocks(ctx, n_pad, cached);
+}
+
 template <int METHOD>
 static int launch_method(pcr_ctx* ctx, const LinParams& P) {
-    // variant: tile-cooperative search for spatially sorted scans, per-lane search otherwise
-    // (sub-warp tiles were measured and rejected: the tiles of one warp diverge from each other,
-    //  so their costs add up instead of overlapping -- profiles/r1_notes.md)
-    const bool tile = ctx->scan_sorted && ctx->tile_lanes == 32;
-    const int mb = ctx->min_blocks;                       // 2, 3 or 4 resident blocks per SM requested
-    const bool flat = !tile && ctx->search_mode == 1;
-    const int v = flat ? (mb >= 4 ? 7 : (mb == 3 ? 6 : 5)) : tile ? (mb >= 3 ? 1 : 0) : (mb >= 4 ? 4 : (mb == 3 ? 3 : 2));
-    int& per_sm = ctx->lin_blocks_per_sm[METHOD][v];
-    if (per_sm == 0) {
-        switch (v) {
-            case 0: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 32, 2>); break;
-            case 1: per_sm = blocks_per_sm(linearize_tile_kernel<METHOD, 32, 3>); break;
-            case 2: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 2>); break;
-            case 3: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 3>); break;
-            case 4: per_sm = blocks_per_sm(linearize_lane_kernel<METHOD, 4>); break;
-            case 5: per_sm = blocks_per_sm(linearize_flat_kernel<METHOD, 2>); break;
-            case 6: per_sm = blocks_per_sm(linearize_flat_kernel<METHOD, 3>); break;
-            default: per_sm = blocks_per_sm(linearize_flat_kernel<METHOD, 4>); break;
+    // ctx->min_blocks = resident blocks per SM requested for the correspondence pass (2..6)
+    const int mb = ctx->min_blocks < 3 ? 3 : (ctx->min_blocks > 6 ? 6 : ctx->min_blocks);
+    int* cache = ctx->lin_blocks_per_sm[METHOD];
+    if (ctx->split_passes) {
+        int blocks;
+        switch (mb) {
+            case 3: blocks = blocks_for_kernel(ctx, correspond_kernel<METHOD, 3>, cache[3], P.n_pad); correspond_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+            case 4: blocks = blocks_for_kernel(ctx, correspond_kernel<METHOD, 4>, cache[4], P.n_pad); correspond_kernel<METHOD, 4><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+            case 5: blocks = blocks_for_kernel(ctx, correspond_kernel<METHOD, 5>, cache[5], P.n_pad); correspond_kernel<METHOD, 5><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
+            default: blocks = blocks_for_kernel(ctx, correspond_kernel<METHOD, 6>, cache[6], P.n_pad); correspond_kernel<METHOD, 6><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
         }
+        PCR_LAUNCH_CHECK();
+        blocks = blocks_for_kernel(ctx, accumulate_kernel<METHOD>, cache[0], P.n_pad);
+        accumulate_kernel<METHOD><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
+        PCR_LAUNCH_CHECK();
+        return PCR_OK;
     }
-    const int blocks = lin_grid_blocks(ctx, P.n_pad, per_sm);
-    switch (v) {
-        case 0: linearize_tile_kernel<METHOD, 32, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 1: linearize_tile_kernel<METHOD, 32, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 2: linearize_lane_kernel<METHOD, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 3: linearize_lane_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 4: linearize_lane_kernel<METHOD, 4><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 5: linearize_flat_kernel<METHOD, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        case 6: linearize_flat_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-        default: linearize_flat_kernel<METHOD, 4><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
-    }
+    const int blocks = blocks_for_kernel(ctx, linearize_fused_kernel<METHOD, 3>, cache[7], P.n_pad);
+    linearize_fused_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
     PCR_LAUNCH_CHECK();
     return PCR_OK;
 }
@@ -917,29 +775,6 @@ int pcr_align(pcr_ctx* ctx, int method, const double T0[16], int max_iter, doubl
     return PCR_OK;
 }
 
-int pcr_debug_tile_nn(pcr_ctx* ctx, int which, const double T[16], double max_dist, double r0, int64_t* idx, float* dist) {
-    if (!ctx || !T || !idx || !dist) return PCR_ERR_ARG;
-    PCR_CUDA(cudaSetDevice(ctx->device));
-    const Grid& g = which == 0 ? ctx->tgt_grid : ctx->vox_grid;
-    if (!g.built) return fail(ctx, PCR_ERR_STATE, "pcr_debug_tile_nn: index not built");
-    if (!ctx->scan_set || ctx->n_scan == 0) return fail(ctx, PCR_ERR_STATE, "pcr_debug_tile_nn: scan not set");
-    LinParams P{};
-    fill_params(ctx, which == 0 ? PCR_ICP : PCR_VPLANE, max_dist, P);
-    memcpy(P.T_param, T, sizeof(double) * 16);
-    P.use_param_T = 1; P.r0_param = (float)r0;
-    DevBuf di, dd;
-    PCR_CUDA(di.ensure((size_t)ctx->n_scan_pad * 8));
-    PCR_CUDA(dd.ensure((size_t)ctx->n_scan_pad * 4));
-    const int blocks = lin_grid_blocks(ctx, P.n_pad, 2);
-    tile_nn_debug_kernel<32><<<blocks, kLinThreads, 0, ctx->stream>>>(P, di.as<long long>(), dd.as<float>());
-    PCR_LAUNCH_CHECK();
-    PCR_CUDA(cudaMemcpyAsync(idx, di.p, (size_t)ctx->n_scan * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaMemcpyAsync(dist, dd.p, (size_t)ctx->n_scan * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-    di.release(); dd.release();
-    return PCR_OK;
-}
-
 int pcr_debug_matches(pcr_ctx* ctx, int which, int64_t* idx) {
     if (!ctx || !idx) return PCR_ERR_ARG;
     PCR_CUDA(cudaSetDevice(ctx->device));
@@ -954,24 +789,6 @@ int pcr_debug_matches(pcr_ctx* ctx, int which, int64_t* idx) {
     PCR_CUDA(cudaMemcpyAsync(idx, di.p, (size_t)ctx->n_scan * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     di.release();
-    return PCR_OK;
-}
-
-int pcr_set_tile_lanes(pcr_ctx* ctx, int lanes) {
-    if (!ctx) return PCR_ERR_ARG;
-    if (lanes != 0 && lanes != 32) return fail(ctx, PCR_ERR_ARG, "pcr_set_tile_lanes: lanes must be 0 (per-point search) or 32 (warp-cooperative search)");
-    ctx->tile_lanes = lanes;
-    return PCR_OK;
-}
-
-int pcr_set_search_mode(pcr_ctx* ctx, int mode, int ch, int tau) {
-    if (!ctx) return PCR_ERR_ARG;
-    if (mode != 0 && mode != 1) return fail(ctx, PCR_ERR_ARG, "pcr_set_search_mode: mode must be 0 (nested) or 1 (flat)");
-    if (ch > 0 && ch < 4) return fail(ctx, PCR_ERR_ARG, "pcr_set_search_mode: ch must be >= 4");
-    if (tau > 32) return fail(ctx, PCR_ERR_ARG, "pcr_set_search_mode: tau must be <= 32");
-    ctx->search_mode = mode;
-    if (ch > 0) ctx->flat_ch = ch;
-    if (tau > 0) ctx->flat_tau = tau;
     return PCR_OK;
 }
 

@@ -76,3 +76,25 @@ class VoxelGrid:
 def voxel_filter(points, voxel_size, device=None):
     """Per-voxel centroid down-sampling, float32 (voxel.py:209-241), on the GPU."""
     return _lib.Context(device).voxel_filter(points, voxel_size)
+
+
+def color_by_voxel(points, voxel_size, device=None):
+    """Structured array ``[('xyz', '<f4', (3,)), ('irgb', '<u4')]`` colouring every point by its voxel
+    (voxel.py:183-206).  Voxel membership comes from the GPU (exact integer coordinates); the
+    colour table is the reference's (``np.random.seed(42)``, one colour per voxel in ascending order of
+    the reference's hash key), so the result equals the reference's whenever that hash has no
+    collision on the data (quirk Q9)."""
+    pts = np.asarray(points)
+    labels, coords = _lib.Context(device).voxel_labels(pts, voxel_size)
+    c = coords.astype(np.int64)
+    p, m = 116101, 10000000000
+    keys = ((c[:, 2] * p % m + c[:, 1]) * p) % m + c[:, 0]            # get_keys on the voxel coordinates
+    rank = np.empty(len(keys), dtype=np.int64)
+    rank[np.argsort(keys, kind="stable")] = np.arange(len(keys))      # position of each voxel in np.unique(keys)
+    state = np.random.get_state()
+    np.random.seed(42)
+    colors = np.random.randint(0, 256, size=(len(keys), 3), dtype=np.uint8)
+    np.random.set_state(state)
+    pc = colors[rank[labels]]
+    rgb = pc[:, 0].astype(np.uint32) << 16 | pc[:, 1].astype(np.uint32) << 8 | pc[:, 2].astype(np.uint32)
+    return np.rec.fromarrays([pts.astype(np.float32), rgb], dtype=[('xyz', '<f4', (3,)), ('irgb', '<u4')])

@@ -10,7 +10,6 @@
 
 #include "../../point_cloud_registration_b200/csrc/pcr_common.cuh"
 #include "../../point_cloud_registration_b200/csrc/pcr_grid.cuh"
-#include "../../point_cloud_registration_b200/csrc/pcr_flat_search.cuh"
 #include "../../point_cloud_registration_b200/csrc/pcr_linalg.cuh"
 #include "../../point_cloud_registration_b200/csrc/pcr_terms.cuh"
 
@@ -274,154 +273,6 @@ void hs_shell_study(void* gp, const float* q, int64_t m, double max_dist, double
             mx = std::max(mx, groups);
         }
         out[0] += (double)mx;
-    }
-}
-
-// Single-lane replay of the resumable search (pcr_flat_search.cuh).
-void hs_flat_nn(void* gp, const float* q, int64_t m, double max_dist, int ch, int64_t* idx, float* dist) {
-    const GridView& G = ((HostGrid*)gp)->v;
-    const float md = (float)max_dist;
-    for (int64_t i = 0; i < m; ++i) {
-        float d2;
-        int pos = flat_nn(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, ch);
-        if (pos >= 0) {
-            uint32_t j;
-            memcpy(&j, &G.pts[pos].w, 4);
-            idx[i] = j; dist[i] = sqrtf(d2);
-        } else { idx[i] = -1; dist[i] = INFINITY; }
-    }
-}
-
-struct CountBest1 {
-    float d2; int pos; long long evals;
-    bool have() const { return pos >= 0; }
-    float radius2() const { return d2; }
-    void offer(float c, int p) { ++evals; if (c < d2) { d2 = c; pos = p; } }
-};
-
-// Lock-step replay of the warp loop of linearize_flat_kernel (pass 1): `threads` persistent
-// lanes, lane t owns queries t, t + threads, ...; 32 consecutive lanes form a warp that runs
-// rounds of { phase A: find work / refill | phase B: evaluate <= ch candidates }.
-// stats: [0] rounds, [1] sum over rounds of max-lane B candidates, [2] sum over rounds of max-lane
-// A steps (cells looked up + passes planned + queries begun), [3] total candidates evaluated (flat),
-// [4] nested baseline: sum over rows of max-lane candidates, [5] nested baseline total candidates,
-// [6] total lane A steps
-void hs_flat_warp_sim(void* gp, const float* q, int64_t m, double max_dist, int ch, int64_t threads,
-                      int64_t* idx, float* dist, double* stats, int tau, int skip_nested) {
-    const GridView& G = ((HostGrid*)gp)->v;
-    const float md2 = (float)max_dist * (float)max_dist;
-    for (int s = 0; s < 8; ++s) stats[s] = 0;
-    const int64_t m_pad = (m + 31) / 32 * 32;
-    std::vector<int> result(m_pad, -2);
-    std::vector<float> result_d2(m_pad, 0.f);
-    for (int64_t w0 = 0; w0 < threads; w0 += 32) {
-        FlatLane L[32];
-        int64_t cur[32];
-        bool active[32], done[32];
-        for (int l = 0; l < 32; ++l) { cur[l] = w0 + l; active[l] = false; done[l] = false; L[l].p = L[l].e = 0; }
-        for (;;) {
-            int maxA = 0;
-            bool all_done = true;
-            int n_need = 0, n_have = 0;
-            for (int l = 0; l < 32; ++l) {
-                if (done[l]) continue;
-                if (L[l].p == L[l].e) ++n_need; else ++n_have;
-            }
-            const bool runA = n_need >= tau || n_have == 0;
-            if (runA) stats[7] += 1;
-            for (int l = 0; l < 32; ++l) {
-                int a = 0;
-                if (!done[l] && runA) {
-                    while (L[l].p == L[l].e) {
-                        if (active[l]) {
-                            ++a;
-                            if (flat_next_cell(G, L[l])) break;
-                            if (flat_next_pass(G, L[l])) continue;
-                            result[cur[l]] = L[l].best_pos; result_d2[cur[l]] = L[l].best_d2;
-                            cur[l] += threads; active[l] = false;
-                        }
-                        if (cur[l] >= m_pad) { done[l] = true; break; }
-                        ++a;
-                        const int64_t i = cur[l];
-                        const float nanv = NAN;
-                        const float x = i < m ? q[3 * i] : nanv, y = i < m ? q[3 * i + 1] : nanv, z = i < m ? q[3 * i + 2] : nanv;
-                        if (flat_begin(G, L[l], x, y, z, md2)) active[l] = true;
-                        else { result[i] = -1; cur[l] += threads; }
-                    }
-                }
-                stats[6] += a;
-                maxA = std::max(maxA, a);
-                all_done = all_done && done[l];
-            }
-            stats[2] += maxA;
-            if (all_done) break;
-            int maxB = 0;
-            for (int l = 0; l < 32; ++l) {
-                if (done[l]) continue;
-                const int n = (int)std::min<uint32_t>(L[l].e - L[l].p, (uint32_t)ch);
-                const int n4 = (n + 3) / 4 * 4;
-                maxB = std::max(maxB, n4);
-                stats[3] += n4;
-                flat_eval(G, L[l], ch);
-            }
-            stats[0] += 1;
-            stats[1] += maxB;
-        }
-    }
-    for (int64_t i = 0; i < m; ++i) {
-        const int pos = result[i];
-        if (pos >= 0) {
-            uint32_t j;
-            memcpy(&j, &G.pts[pos].w, 4);
-            idx[i] = j; dist[i] = sqrtf(result_d2[i]);
-        } else { idx[i] = pos == -1 ? -1 : -2; dist[i] = INFINITY; }
-    }
-    // nested baseline (grid_search): candidates per query, rows of 32 consecutive queries
-    for (int64_t r = 0; r < m && !skip_nested; r += 32) {
-        long long mx = 0;
-        for (int64_t i = r; i < std::min(m, r + 32); ++i) {
-            CountBest1 b; b.d2 = md2; b.pos = -1; b.evals = 0;
-            grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], b);
-            mx = std::max(mx, b.evals);
-            stats[5] += (double)b.evals;
-        }
-        stats[4] += (double)mx;
-    }
-}
-
-
-// Development aid: candidates evaluated per query by the flat search when the pruning radius
-// starts at (a) max_dist, (b) the true NN distance (perfect bound), (c) the distance to the NN of
-// the query's cell centre ("seed" bound).  out[3] = totals.
-void hs_bound_study(void* gp, const float* q, int64_t m, double max_dist, double* out) {
-    const GridView& G = ((HostGrid*)gp)->v;
-    const float md2 = (float)max_dist * (float)max_dist;
-    out[0] = out[1] = out[2] = 0;
-    for (int64_t i = 0; i < m; ++i) {
-        const float qx = q[3 * i], qy = q[3 * i + 1], qz = q[3 * i + 2];
-        float d2true;
-        int pos = grid_nn(G, qx, qy, qz, md2, d2true);
-        // seed: NN of the centre of the query's cell
-        const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
-        const float cx = (floorf(gx) + 0.5f) * G.h + G.ox, cy = (floorf(gy) + 0.5f) * G.h + G.oy, cz = (floorf(gz) + 0.5f) * G.h + G.oz;
-        float dseed;
-        int spos = grid_nn(G, cx, cy, cz, 3.0e38f, dseed);
-        float seed_d2 = md2;
-        if (spos >= 0) {
-            const float4 t = G.pts[spos];
-            const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-            seed_d2 = std::min(md2, (ex * ex + ey * ey + ez * ez) * 1.00001f + 1e-12f);
-        }
-        const float starts[3] = {md2, pos >= 0 ? d2true * 1.00001f + 1e-12f : md2, seed_d2};
-        for (int v = 0; v < 3; ++v) {
-            FlatLane L;
-            long long cnt = 0;
-            if (flat_begin(G, L, qx, qy, qz, starts[v])) {
-                if (v > 0) L.best_pos = 0;     // pretend a candidate exists: the first pass after the own cell is the ball pass
-                while (flat_find_work(G, L)) { cnt += (L.e - L.p); flat_eval(G, L, 1 << 20); }
-            }
-            out[v] += (double)cnt;
-        }
     }
 }
 

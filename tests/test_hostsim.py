@@ -31,9 +31,6 @@ def hs():
     lib.hs_grid_cells.restype = C.c_int64
     lib.hs_grid_cells.argtypes = [C.c_void_p]
     lib.hs_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
-    lib.hs_flat_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
-    lib.hs_flat_warp_sim.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_int, C.c_int]
     lib.hs_shell_build.restype = C.c_int64
     lib.hs_shell_build.argtypes = [C.c_void_p, C.c_double]
     lib.hs_shell_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -133,34 +130,6 @@ def test_nn_degenerate(hs):
     assert idx[0] == -1 and idx[1] == -1 and idx[2] >= 0
     big = (rng.random((2000, 3)) * 800 - 400).astype(np.float32)      # large coordinates
     check_nn(hs, big, (rng.random((500, 3)) * 900 - 450).astype(np.float32), 25.0)
-
-
-@pytest.mark.parametrize("ch,tau,threads", [(8, 1, 64), (32, 1, 256), (16, 16, 96), (4, 32, 32)])
-def test_flat_search_matches_nested(hs, ch, tau, threads):
-    """The resumable search (pcr_flat_search.cuh) -- single lane and in the lock-step replay of the
-    kernel's warp loop (rounds, refill, phase-A threshold) -- returns exactly what grid_search()
-    returns: near, far (ring growth), outside the grid, NaN, tight max_dist, coarse and fine cells."""
-    rng = np.random.default_rng(4)
-    pts = ds.make_urban_slab(20000, seed=7)
-    near = ds.perturb_scan(pts, seed=3)[:3001]
-    far = near[:700] + np.array([0, 0, 3.0], dtype=np.float32)
-    box = (rng.random((800, 3)) * (pts.max(0) - pts.min(0) + 6) + pts.min(0) - 3).astype(np.float32)
-    bad = near[:40].copy()
-    bad[::5, 1] = np.nan
-    for h in (0.08, 0.3, 1.5):
-        g = hs.hs_grid_build(ptr(pts), len(pts), float(h))
-        for q, md in ((near, 2.0), (near, 0.03), (far, 2.0), (far, 1e9), (box, 2.0), (bad, 2.0)):
-            q = np.ascontiguousarray(q)
-            i0 = np.empty(len(q), np.int64); d0 = np.empty(len(q), np.float32)
-            hs.hs_nn(g, ptr(q), len(q), float(md), ptr(i0), ptr(d0))
-            i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32)
-            hs.hs_flat_nn(g, ptr(q), len(q), float(md), ch, ptr(i1), ptr(d1))
-            i2 = np.empty(len(q), np.int64); d2 = np.empty(len(q), np.float32); st = np.zeros(8)
-            hs.hs_flat_warp_sim(g, ptr(q), len(q), float(md), ch, threads, ptr(i2), ptr(d2), ptr(st), tau, 1)
-            assert np.array_equal(d0, d1) and np.array_equal(d0, d2)
-            assert (i0 == i1).mean() > 0.999 and (i0 == i2).mean() > 0.999 and not np.any(i2 == -2)
-            assert np.array_equal(i0 < 0, i1 < 0) and np.array_equal(i0 < 0, i2 < 0)
-        hs.hs_grid_free(g)
 
 
 @pytest.mark.parametrize("dmax_frac", [1.0, 0.5, 1.7])
