@@ -222,9 +222,11 @@ int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, Dev
         for (;;) {   // enlarge h until the dense brick table fits
             V.h = (float)h;
             V.inv_h = (float)(1.0 / h);
-            V.ox = lo[0] - 0.25f * V.h; V.oy = lo[1] - 0.25f * V.h; V.oz = lo[2] - 0.25f * V.h;
+            // two empty cells of padding around the bounding box: scan points that leave the box by
+            // up to two cells still fall into (band) cells of the grid and get their shell list
+            V.ox = lo[0] - 2.25f * V.h; V.oy = lo[1] - 2.25f * V.h; V.oz = lo[2] - 2.25f * V.h;
             double c[3];
-            for (int a = 0; a < 3; ++a) c[a] = floor(((double)hi[a] - (double)(lo[a] - 0.25f * V.h)) / h) + 2.0;
+            for (int a = 0; a < 3; ++a) c[a] = floor(((double)hi[a] - (double)(lo[a] - 2.25f * V.h)) / h) + 4.0;
             V.bnx = (int)std::min(c[0] / 4.0 + 1.0, 2.0e9); V.bny = (int)std::min(c[1] / 4.0 + 1.0, 2.0e9); V.bnz = (int)std::min(c[2] / 4.0 + 1.0, 2.0e9);
             nbricks = (unsigned long long)V.bnx * V.bny * V.bnz;
             if ((double)V.bnx * V.bny * V.bnz <= (double)kMaxBricks && V.bnx < (1 << 20) && V.bny < (1 << 20) && V.bnz < (1 << 20)) break;
@@ -604,8 +606,8 @@ static int voxel_front(pcr_ctx* ctx, const void* xyz, long long n, double voxel_
 // ---------------------------------------------------------------------------------------
 // per-cell candidate lists over the kept voxel means (see CandLists in pcr_common.cuh)
 // ---------------------------------------------------------------------------------------
-// ctx->list_dilate (default 2): cells within this Chebyshev distance of a kept voxel get a list
-// ctx->list_radius (default 3): the build looks at the (2R+1)^3 neighbourhood; exact while D_C < R
+// ctx->list_dilate (default 3): cells within this Chebyshev distance of a kept voxel get a list
+// ctx->list_radius (default 5): the build looks at the (2R+1)^3 neighbourhood; exact while D_C < R
 
 // mark the neighbourhood of every kept voxel as "band" (cells that get a list)
 __global__ void band_mark_kernel(GridView G, BrickRec* __restrict__ lbricks, int dilate) {
@@ -768,8 +770,11 @@ static int build_voxel_lists(pcr_ctx* ctx) {
 // ---------------------------------------------------------------------------------------
 // per-cell shell lists over the target-point grid (see ShellLists in pcr_common.cuh)
 // ---------------------------------------------------------------------------------------
-// level j >= 1 holds margins in (frac[j-1], frac[j]] cell edges (cut at dmax); level 0 = the cell's own points
-__constant__ float kShellFrac[PCR_SHELL_LEVELS] = {0.0f, 0.03125f, 0.0625f, 0.125f, 0.1768f, 0.25f, 0.3536f, 0.5f, 0.7071f, 1.0f, 1.4142f, 2.0f};
+// level j >= 1 holds margins in (frac[j-1], frac[j]] cell edges (cut at dmax), frac growing by
+// 2^(1/4) per level up to 2 cell edges; level 0 = the cell's own points
+__constant__ float kShellFrac[PCR_SHELL_LEVELS] = {
+    0.0f, 0.0442f, 0.0526f, 0.0625f, 0.0743f, 0.0884f, 0.1051f, 0.125f, 0.1487f, 0.1768f, 0.2102f, 0.25f,
+    0.2973f, 0.3536f, 0.4204f, 0.5f, 0.5946f, 0.7071f, 0.8409f, 1.0f, 1.1892f, 1.4142f, 1.6818f, 2.0f};
 
 // One thread per (brick, bit) of the band.  FILL = false: counts[ordinal] = list length padded to
 // a multiple of four; FILL = true: write the entries level by level, the sentinels and the
@@ -833,7 +838,9 @@ __global__ void shell_build_kernel(GridView G, const BrickRec* __restrict__ band
                     uint32_t w = 0;
 #pragma unroll
                     for (int l = 0; l < PCR_SHELL_LEVELS; ++l) if (l == lvl) w = cnt[l]++;
-                    out[base + w] = make_float4(t.x, t.y, t.z, __uint_as_float(p));
+                    float* grp = reinterpret_cast<float*>(out + base + (w & ~3u));   // group of four, structure of arrays
+                    const uint32_t j = w & 3u;
+                    grp[j] = t.x; grp[4 + j] = t.y; grp[8 + j] = t.z; grp[12 + j] = __uint_as_float(p);
                 }
             }
         }
@@ -858,7 +865,11 @@ __global__ void shell_build_kernel(GridView G, const BrickRec* __restrict__ band
                 else if (l_of >= 1) lb = fmaxf(kShellFrac[l_of - 1] * G.h - slack_w, 0.0f);
                 margin2[(base + g4) >> 2] = lb * lb;
             }
-            for (uint32_t k = total; k < padded; ++k) out[base + k] = make_float4(3.0e38f, 3.0e38f, 3.0e38f, __uint_as_float(0xffffffffu));
+            for (uint32_t k = total; k < padded; ++k) {       // sentinels complete the last group
+                float* grp = reinterpret_cast<float*>(out + base + (k & ~3u));
+                const uint32_t j = k & 3u;
+                grp[j] = 3.0e38f; grp[4 + j] = 3.0e38f; grp[8 + j] = 3.0e38f; grp[12 + j] = __uint_as_float(0xffffffffu);
+            }
             uint32_t run = 0;
 #pragma unroll
             for (int l = 0; l < PCR_SHELL_LEVELS; ++l) { const uint32_t c = cnt[l]; cnt[l] = run; run += c; }
@@ -1112,8 +1123,9 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_SHELL_DMAX")) ctx->shell_dmax_frac = atof(e) > 0.0 && atof(e) <= 2.0 ? atof(e) : 1.0;
     if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 24.0;
     if (const char* e = getenv("PCR_QUEUE")) ctx->use_queue = atoi(e) != 0;
-    if (const char* e = getenv("PCR_LIST_DILATE")) ctx->list_dilate = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 2;
-    if (const char* e = getenv("PCR_LIST_RADIUS")) ctx->list_radius = atoi(e) >= 2 && atoi(e) <= 6 ? atoi(e) : 3;
+    if (const char* e = getenv("PCR_LIST_DILATE")) ctx->list_dilate = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 3;
+    if (const char* e = getenv("PCR_LIST_RADIUS")) ctx->list_radius = atoi(e) >= 2 && atoi(e) <= 6 ? atoi(e) : 5;
+    if (const char* e = getenv("PCR_GRAB_ROWS")) ctx->grab_rows = atoi(e) >= 1 && atoi(e) <= 64 ? atoi(e) : 1;
     if (const char* e = getenv("PCR_SPLIT")) ctx->split_passes = atoi(e) != 0;
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }

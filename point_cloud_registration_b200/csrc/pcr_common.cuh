@@ -107,6 +107,18 @@ PCR_HD double ddiv_rn(double a, double b) {
 #endif
 }
 
+// Squared distance with ONE fixed rounding sequence, ex*ex, then fma(ey, ey, .), then fma(ez, ez, .):
+// every search path (brick-grid walk, candidate lists, shell lists with packed f32x2 arithmetic)
+// computes bit-identical distances, so they all pick the same neighbour.
+PCR_HD float dist2_rn(float ex, float ey, float ez) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(ez, ez, __fmaf_rn(ey, ey, __fmul_rn(ex, ex)));
+#else
+    volatile float xx = ex * ex;
+    return fmaf(ez, ez, fmaf(ey, ey, xx));
+#endif
+}
+
 // --------------------------------------------------------------------------------------
 // Two-level sparse uniform grid ("brick grid") used for every exact nearest-neighbour
 // search (target points for ICP/PlaneICP/kNN normals, kept voxel means for VPlaneICP/NDT).
@@ -151,17 +163,20 @@ struct CandLists {
 // Per-cell "shell lists" over the target-point grid.  For every band cell C (within Chebyshev
 // distance 1 of an occupied cell) ONE contiguous list holds every indexed point whose distance to
 // the box of C (its "margin") is <= dmax, ordered by margin level: level 0 = the points binned in
-// C itself, levels 1.. = shells of growing margin.  Entries are float4 (x, y, z, position of the
-// point in GridView::pts); lists are padded to a multiple of four with sentinels, and for every
-// group of four `margin2[group]` is a lower bound of the squared margin of the group's and of all
-// later entries.  A query in C then needs no geometry at all:
+// C itself, levels 1.. = shells of growing margin.  Lists are padded to a multiple of four with
+// sentinels and stored in groups of four entries, structure-of-arrays inside the group:
+//     pts[4g] = (x0 x1 x2 x3), pts[4g+1] = (y0 ..), pts[4g+2] = (z0 ..), pts[4g+3] = positions of the
+//     four points in GridView::pts (uint32 bits)
+// so that three 16-byte loads feed four distance evaluations in packed f32x2 arithmetic and the
+// positions are only read for the winner.  For every group `margin2[group]` is a lower bound of the
+// squared margin of the group's and of all later entries.  A query in C needs no geometry at all:
 //     for each group: if (margin2[group] >= best) stop;  evaluate the four entries
 // -- a point not yet looked at is at least its margin away from any location in C -- and every
 // query of one cell streams the SAME addresses for (nearly) the SAME number of steps, which is
 // what the per-lane searches over cell walks could not offer (10-13 active lanes per warp
 // instruction, the rest waiting for stragglers).  If the list ends while the best is still
 // farther than dmax, the general search takes over from that bound.
-#define PCR_SHELL_LEVELS 12
+#define PCR_SHELL_LEVELS 24
 struct ShellLists {
     const uint4* bricks;         // (band mask lo, hi, ordinal of first band cell, unused), brick layout of the grid
     const uint32_t* start;       // [n_band + 1], multiples of 4

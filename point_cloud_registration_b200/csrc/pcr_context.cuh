@@ -9,11 +9,20 @@
 #include "../../include/pcr_b200.h"
 #include "pcr_common.cuh"
 
+#ifndef PCR_ACC_BATCH
+#define PCR_ACC_BATCH 2
+#endif
+#ifndef PCR_ACC_MINB
+#define PCR_ACC_MINB 3
+#endif
+
 namespace pcr {
 
 constexpr int kMaxTrace = 256;          // per-iteration e2 trace capacity of the on-device GN loop
 constexpr int kLinThreads = 256;        // threads per block of the linearise kernels
 constexpr int kMaxLinBlocks = 148 * 8;  // upper bound on persistent grid size (partials buffer)
+constexpr int kAccBatch = PCR_ACC_BATCH;     // scan slots whose gathers are in flight together in the accumulate pass
+constexpr int kAccMinBlocks = PCR_ACC_MINB;  // resident blocks per SM requested for the accumulate kernel
 constexpr int kQueueCap = 6144;         // per-block straggler queue of the linearise kernel (24 KB of shared memory)
 
 // Device-resident Gauss-Newton loop state (one per context).
@@ -26,7 +35,7 @@ struct LoopState {
     int iter;               // linearisations executed so far
     int done;               // 0 running, 1 converged, 2 singular H
     unsigned int ticket;    // block arrival counter of the running linearise kernel
-    float reserved;
+    int next_row;           // next unassigned row of 32 scan slots of the running correspondence pass
 };
 
 struct DevBuf {
@@ -89,7 +98,7 @@ struct pcr_ctx {
     pcr::CandLists vox_lists{};   // null pointers = not built
     long long n_band_cells = 0, n_list_entries = 0;
     int use_voxel_lists = 1;
-    int list_dilate = 2, list_radius = 3;   // candidate-list band dilation / build neighbourhood radius (cells)
+    int list_dilate = 3, list_radius = 5;   // candidate-list band dilation / build neighbourhood radius (cells)
     pcr::DevBuf vox_rec_plane;    // float4[2n]: (mean, 0), (normal, 0)
     pcr::DevBuf vox_rec_ndt;      // float4[3n]: (mean, W00), (W01, W02, W11, W12), (W22, 0, 0, 0)
     bool has_voxels = false, has_icov = false;
@@ -101,6 +110,7 @@ struct pcr_ctx {
     bool scan_sorted = false;     // spatially coherent order (Morton-sorted on upload, or promised by the caller)
     double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
     int min_blocks = 4;           // resident blocks per SM requested for the correspondence pass (3..6)
+    int grab_rows = 1;            // rows of 32 scan slots a warp fetches at a time
     int split_passes = 1;         // 1: correspond + accumulate kernels, 0: one fused kernel (A/B)
     int lin_blocks_per_sm[4][9] = {};   // cached occupancy per (method, kernel variant)
     pcr::DevBuf scan_x, scan_y, scan_z;

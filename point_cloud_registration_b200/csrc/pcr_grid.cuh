@@ -97,7 +97,7 @@ PCR_HD void visit_block(const GridView& G, float qx, float qy, float qz, float g
                     for (uint32_t p = s; p < e; ++p) {
                         const float4 t = G.pts[p];
                         const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-                        best.offer(ex * ex + ey * ey + ez * ez, (int)p);
+                        best.offer(dist2_rn(ex, ey, ez), (int)p);
                     }
                 }
             }
@@ -140,7 +140,7 @@ PCR_HD void visit_small_box(const GridView& G, float qx, float qy, float qz, flo
                     for (uint32_t p = s; p < e; ++p) {
                         const float4 t = G.pts[p];
                         const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-                        best.offer(ex * ex + ey * ey + ez * ez, (int)p);
+                        best.offer(dist2_rn(ex, ey, ez), (int)p);
                     }
                 }
             }
@@ -242,6 +242,30 @@ PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2
     return b.pos;
 }
 
+// Four squared distances of one structure-of-arrays group (see ShellLists) to the query, in packed
+// f32x2 arithmetic on sm_100 (same roundings as dist2_rn); updates the best and its list offset.
+PCR_HD void shell_eval_group(const float4& X, const float4& Y, const float4& Z, float qx, float qy, float qz, uint32_t k,
+                             float& best, uint32_t& best_k) {
+    float d0, d1, d2, d3;
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    const float2 nx = make_float2(-qx, -qx), ny = make_float2(-qy, -qy), nz = make_float2(-qz, -qz);
+    const float2 ex01 = __fadd2_rn(make_float2(X.x, X.y), nx), ex23 = __fadd2_rn(make_float2(X.z, X.w), nx);
+    const float2 ey01 = __fadd2_rn(make_float2(Y.x, Y.y), ny), ey23 = __fadd2_rn(make_float2(Y.z, Y.w), ny);
+    const float2 ez01 = __fadd2_rn(make_float2(Z.x, Z.y), nz), ez23 = __fadd2_rn(make_float2(Z.z, Z.w), nz);
+    const float2 r01 = __ffma2_rn(ez01, ez01, __ffma2_rn(ey01, ey01, __fmul2_rn(ex01, ex01)));
+    const float2 r23 = __ffma2_rn(ez23, ez23, __ffma2_rn(ey23, ey23, __fmul2_rn(ex23, ex23)));
+    d0 = r01.x; d1 = r01.y; d2 = r23.x; d3 = r23.y;
+#else
+    d0 = dist2_rn(X.x - qx, Y.x - qy, Z.x - qz); d1 = dist2_rn(X.y - qx, Y.y - qy, Z.y - qz);
+    d2 = dist2_rn(X.z - qx, Y.z - qy, Z.z - qz); d3 = dist2_rn(X.w - qx, Y.w - qy, Z.w - qz);
+#endif
+    const float dm = fminf(fminf(d0, d1), fminf(d2, d3));
+    if (dm < best) {                                          // rare after the first groups
+        best = dm;
+        best_k = k + (dm == d0 ? 0u : (dm == d1 ? 1u : (dm == d2 ? 2u : 3u)));
+    }
+}
+
 // Stream the shell list (see ShellLists) of the query's cell.  Returns
 //   0  the cell has no list: nothing was looked at, the caller must run the general search;
 //   1  final: out_d2 / out_pos hold the exact nearest neighbour (or -1: none within max_dist);
@@ -258,36 +282,34 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
     const uint32_t ord = rec.z + (uint32_t)popc64(band & ((1ull << bit) - 1ull));
     const uint32_t s = S.start[ord], e = S.start[ord + 1];
     float best = max_d2;
-    float best_w = 0.0f;
-    bool have = false, exhausted = true;
-    // software pipeline: the next group of four (and its margin bound) is in flight while the
-    // current one is evaluated; reading one group past the end is safe (the next list or the
-    // sentinels that terminate the array) and its values are never used
-    uint32_t k = s;
-    float m = S.margin2[k >> 2];
-    float4 t0 = S.pts[k], t1 = S.pts[k + 1], t2 = S.pts[k + 2], t3 = S.pts[k + 3];
-    while (k < e) {
+    uint32_t best_k = 0xffffffffu;                            // list offset of the best entry
+    bool exhausted = true;
+    // One group per trip: margin bound of the NEXT group is requested together with the three
+    // vectors of this one (reading one bound past the end is safe and never used).  Deeper software
+    // pipelining was measured: no gain -- the loads hit L1 and other warps cover their latency.
+    const float4* p = S.pts + s;
+    const float4* const pe = S.pts + e;
+    const float* mp = S.margin2 + (s >> 2);
+    float m = mp[0];
+    while (p < pe) {
         if (m >= best) { exhausted = false; break; }          // everything from here on is at least this far
-        const float4 c0 = t0, c1 = t1, c2 = t2, c3 = t3;
-        k += 4;
-        m = S.margin2[k >> 2];
-        t0 = S.pts[k]; t1 = S.pts[k + 1]; t2 = S.pts[k + 2]; t3 = S.pts[k + 3];
-        float ex, ey, ez, d;
-        ex = c0.x - qx; ey = c0.y - qy; ez = c0.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = c0.w; have = true; }
-        ex = c1.x - qx; ey = c1.y - qy; ez = c1.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = c1.w; have = true; }
-        ex = c2.x - qx; ey = c2.y - qy; ez = c2.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = c2.w; have = true; }
-        ex = c3.x - qx; ey = c3.y - qy; ez = c3.z - qz; d = ex * ex + ey * ey + ez * ez;
-        if (d < best) { best = d; best_w = c3.w; have = true; }
+        const float4 X = p[0], Y = p[1], Z = p[2];
+        m = mp[1];
+        shell_eval_group(X, Y, Z, qx, qy, qz, (uint32_t)(p - S.pts), best, best_k);
+        p += 4; ++mp;
     }
     out_d2 = best;
+    out_pos = -1;
+    if (best_k != 0xffffffffu) {
+        const float4 W = S.pts[(best_k & ~3u) + 3u];
+        const uint32_t j = best_k & 3u;
+        const float w = j == 0u ? W.x : (j == 1u ? W.y : (j == 2u ? W.z : W.w));
 #if defined(__CUDA_ARCH__)
-    out_pos = have ? __float_as_int(best_w) : -1;
+        out_pos = __float_as_int(w);
 #else
-    { int w; memcpy(&w, &best_w, 4); out_pos = have ? w : -1; }
+        memcpy(&out_pos, &w, 4);
 #endif
+    }
     // stopped by a margin bound: final.  List exhausted: final only if the best (or, with no
     // candidate, the search radius) lies within the covered margin.
     return (exhausted && !(best <= S.covered2)) ? 2 : 1;
@@ -326,7 +348,7 @@ PCR_HD bool list_nn(const GridView& G, const CandLists& L, float qx, float qy, f
         const uint32_t p = L.list_idx[k];
         const float4 t = G.pts[p];
         const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-        const float d2 = ex * ex + ey * ey + ez * ez;
+        const float d2 = dist2_rn(ex, ey, ez);
         if (d2 < best) { best = d2; pos = (int)p; }
     }
     out_d2 = best;
@@ -341,7 +363,7 @@ PCR_HD int grid_nn_warm(const GridView& G, float qx, float qy, float qz, float m
     if (warm_pos >= 0) {
         const float4 t = G.pts[warm_pos];
         const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-        const float dw = ex * ex + ey * ey + ez * ez;
+        const float dw = dist2_rn(ex, ey, ez);
         if (dw < max_d2) { b.d2 = dw; b.pos = warm_pos; }
     }
     grid_search(G, qx, qy, qz, b);

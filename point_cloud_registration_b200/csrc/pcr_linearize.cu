@@ -37,6 +37,7 @@ struct LinParams {
     int use_lists;
     ShellLists shell;                                    // ICP/PLANE: per-cell shell lists (null = absent)
     int use_shell;
+    int grab_rows;                                       // rows of 32 scan slots a warp fetches at a time (correspondence pass)
     int use_queue;                                       // park list misses in the block queue (pass 1b) instead of searching in place
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
@@ -61,24 +62,39 @@ struct BlockShared {
     int flag;
 };
 
-// gather the matched record and add this correspondence's terms
+// the matched record (fetched first, for several slots at once, so that the gathers overlap) ...
+struct MatchRec { float4 a, b, c; };
+
 template <int METHOD>
-__device__ __forceinline__ void accumulate_match(const LinParams& P, const Pose32& pose, float* acc, int pos,
-                                                 float px, float py, float pz, float qx, float qy, float qz) {
+__device__ __forceinline__ void fetch_match(const LinParams& P, int pos, MatchRec& r) {
+    if (pos < 0) return;
     if (METHOD == PCR_METHOD_ICP) {
-        const float4 t = __ldg(P.grid.pts + pos);
-        accum_icp(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z);
+        r.a = __ldg(P.grid.pts + pos);
     } else if (METHOD == PCR_METHOD_PLANE) {
-        const float4 t = __ldg(P.grid.pts + pos);
-        const float4 nn = __ldg(P.nrm + pos);
-        accum_plane(acc, pose, px, py, pz, qx - t.x, qy - t.y, qz - t.z, nn.x, nn.y, nn.z);
+        r.a = __ldg(P.grid.pts + pos);
+        r.b = __ldg(P.nrm + pos);
     } else if (METHOD == PCR_METHOD_VPLANE) {
-        const float4 m = __ldg(P.vrec + 2 * (size_t)pos), nn = __ldg(P.vrec + 2 * (size_t)pos + 1);
-        accum_plane(acc, pose, px, py, pz, qx - m.x, qy - m.y, qz - m.z, nn.x, nn.y, nn.z);
+        r.a = __ldg(P.vrec + 2 * (size_t)pos);
+        r.b = __ldg(P.vrec + 2 * (size_t)pos + 1);
     } else {
-        const float4 a = __ldg(P.vrec + 3 * (size_t)pos), b = __ldg(P.vrec + 3 * (size_t)pos + 1), c = __ldg(P.vrec + 3 * (size_t)pos + 2);
-        const float w6[6] = {a.w, b.x, b.y, b.z, b.w, c.x};
-        accum_ndt(acc, pose, px, py, pz, qx - a.x, qy - a.y, qz - a.z, w6);
+        r.a = __ldg(P.vrec + 3 * (size_t)pos);
+        r.b = __ldg(P.vrec + 3 * (size_t)pos + 1);
+        r.c = __ldg(P.vrec + 3 * (size_t)pos + 2);
+    }
+}
+
+// ... and this correspondence's terms
+template <int METHOD>
+__device__ __forceinline__ void accumulate_match(const Pose32& pose, float* acc, const MatchRec& r, float px, float py, float pz) {
+    float qx, qy, qz;
+    transform32(pose, px, py, pz, qx, qy, qz);
+    if (METHOD == PCR_METHOD_ICP) {
+        accum_icp(acc, pose, px, py, pz, qx - r.a.x, qy - r.a.y, qz - r.a.z);
+    } else if (METHOD == PCR_METHOD_PLANE || METHOD == PCR_METHOD_VPLANE) {
+        accum_plane(acc, pose, px, py, pz, qx - r.a.x, qy - r.a.y, qz - r.a.z, r.b.x, r.b.y, r.b.z);
+    } else {
+        const float w6[6] = {r.a.w, r.b.x, r.b.y, r.b.z, r.b.w, r.c.x};
+        accum_ndt(acc, pose, px, py, pz, qx - r.a.x, qy - r.a.y, qz - r.a.z, w6);
     }
 }
 
@@ -94,6 +110,7 @@ __device__ __noinline__ void finish_iteration(const LinParams& P, BlockShared& s
     }
     for (int i = 0; i < PCR_NEQ; ++i) st->rec[i] = rec[i];
     st->ticket = 0u;
+    st->next_row = 0;                                     // every block is past its correspondence pass: re-arm the row counter
     int iter = st->iter;
     int done = 0;
     if (P.device_loop) {
@@ -187,49 +204,74 @@ __device__ __noinline__ int general_nn(const GridView& G, float qx, float qy, fl
 // or the best still beyond the listed margin) are NOT searched here, where they would stall the
 // other 31 lanes of their warp: their scan slots go to a block queue.  1b: the block works the
 // queue off with every lane busy (general brick-grid search).
+// one scan slot: list stream, or a ticket in the block queue
 template <int METHOD>
-__device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32& pose, int* sq, int* sq_len) {
+__device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32& pose, int* sq, int* sq_len, long long i, int lane, bool lists) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
-    const long long stride = (long long)gridDim.x * kLinThreads;
-    const long long first = blockIdx.x * (long long)kLinThreads + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    const bool lists = kVoxel ? (P.use_lists != 0) : (P.use_shell != 0);
-    for (long long i = first; i < P.n_pad; i += stride) {       // n_pad and stride are multiples of 32: warps stay whole
-        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
-        float qx, qy, qz;
-        transform32(pose, px, py, pz, qx, qy, qz);
-        float d2;
-        int pos = -1;
-        bool pending = false;
-        if (lists) {
-            if (px == px) {                                      // NaN = padding: no match
-                if (kVoxel) pending = !list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
-                else pending = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) != 1;
-            }
-            if (P.use_queue) {
-                const unsigned m = __ballot_sync(0xffffffffu, pending);
-                if (m) {
-                    const int leader = __ffs(m) - 1;
-                    int base = 0;
-                    if (lane == leader) base = atomicAdd(sq_len, __popc(m));
-                    base = __shfl_sync(0xffffffffu, base, leader);
-                    if (pending) {
-                        const int slot = base + __popc(m & ((1u << lane) - 1u));
-                        if (slot < kQueueCap) sq[slot] = (int)i;
-                        else pos = general_nn(P.grid, qx, qy, qz, P.max_d2);       // queue full: search in place
-                    }
+    const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+    float qx, qy, qz;
+    transform32(pose, px, py, pz, qx, qy, qz);
+    float d2;
+    int pos = -1;
+    bool pending = false;
+    if (lists) {
+        if (px == px) {                                          // NaN = padding: no match
+            if (kVoxel) pending = !list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
+            else pending = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) != 1;
+        }
+        if (P.use_queue) {
+            const unsigned m = __ballot_sync(0xffffffffu, pending);
+            if (m) {
+                const int leader = __ffs(m) - 1;
+                int base = 0;
+                if (lane == leader) base = atomicAdd(sq_len, __popc(m));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (pending) {
+                    const int slot = base + __popc(m & ((1u << lane) - 1u));
+                    if (slot < kQueueCap) sq[slot] = (int)i;
+                    else pos = general_nn(P.grid, qx, qy, qz, P.max_d2);           // queue full: search in place
                 }
-            } else if (pending) {
-                pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
             }
-        } else if (px == px) {
+        } else if (pending) {
             pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
         }
-        P.prev[i] = pos;
+    } else if (px == px) {
+        pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
+    }
+    P.prev[i] = pos;
+}
+
+// DYNAMIC: warps fetch rows of 32 consecutive scan slots from a device-wide counter (P.grab_rows
+// rows per fetch) -- the cost of a row varies with the local geometry, and a static partition left
+// the slowest SM 30 % behind the average.  The parked result of a slot does not depend on who
+// computed it and the accumulate pass keeps its fixed order, so results stay deterministic.  Only
+// possible when the accumulate pass is a separate kernel (it reads slots parked by other blocks).
+template <int METHOD, bool DYNAMIC>
+__device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32& pose, int* sq, int* sq_len) {
+    constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
+    const int lane = threadIdx.x & 31;
+    const bool lists = kVoxel ? (P.use_lists != 0) : (P.use_shell != 0);
+    if (DYNAMIC) {
+        const int rows_total = (int)(P.n_pad >> 5);
+        for (;;) {
+            int r0 = 0;
+            if (lane == 0) r0 = atomicAdd(&P.st->next_row, P.grab_rows);
+            r0 = __shfl_sync(0xffffffffu, r0, 0);
+            if (r0 >= rows_total) break;
+            const int r1 = r0 + P.grab_rows < rows_total ? r0 + P.grab_rows : rows_total;
+            for (int r = r0; r < r1; ++r) correspond_slot<METHOD>(P, pose, sq, sq_len, ((long long)r << 5) + lane, lane, lists);
+        }
+    } else {
+        const long long stride = (long long)gridDim.x * kLinThreads;   // n_pad and stride are multiples of 32: warps stay whole
+        for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride)
+            correspond_slot<METHOD>(P, pose, sq, sq_len, i, lane, lists);
     }
     __syncthreads();
+    // queue item k goes to lane k / 8 of warp k % 8 (then round again): a short queue is spread over
+    // all warps of the block, whose searches overlap, instead of filling the lanes of one warp
     const int nq = *sq_len < kQueueCap ? *sq_len : kQueueCap;
-    for (int k = threadIdx.x; k < nq; k += kLinThreads) {
+    constexpr int kWarps = kLinThreads / 32;
+    for (int k = (threadIdx.x & 31) * kWarps + (threadIdx.x >> 5); k < nq; k += kLinThreads) {
         const long long i = sq[k];
         const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
         float qx, qy, qz;
@@ -247,13 +289,27 @@ __device__ __forceinline__ void accumulate_pass(const LinParams& P, BlockShared&
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-    for (long long i = first; i < P.n_pad; i += stride) {
-        const int pos = P.prev[i];
-        if (pos < 0) continue;
-        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
-        float qx, qy, qz;
-        transform32(pose, px, py, pz, qx, qy, qz);
-        accumulate_match<METHOD>(P, pose, acc, pos, px, py, pz, qx, qy, qz);
+    // kAccBatch slots per trip: positions, scan points and matched records of all of them are
+    // requested before the first is consumed (the gathers are latency bound); the terms are added
+    // in slot order, so the per-thread summation order does not depend on the batching
+    for (long long i = first; i < P.n_pad; i += kAccBatch * stride) {
+        int pos[kAccBatch];
+        float px[kAccBatch], py[kAccBatch], pz[kAccBatch];
+        MatchRec rec[kAccBatch];
+#pragma unroll
+        for (int u = 0; u < kAccBatch; ++u) {
+            const long long iu = i + u * stride;
+            pos[u] = iu < P.n_pad ? P.prev[iu] : -1;
+        }
+#pragma unroll
+        for (int u = 0; u < kAccBatch; ++u) {
+            const long long iu = i + u * stride;
+            if (pos[u] >= 0) { px[u] = __ldg(P.sx + iu); py[u] = __ldg(P.sy + iu); pz[u] = __ldg(P.sz + iu); }
+            fetch_match<METHOD>(P, pos[u], rec[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kAccBatch; ++u)
+            if (pos[u] >= 0) accumulate_match<METHOD>(pose, acc, rec[u], px[u], py[u], pz[u]);
     }
     reduce_and_finish<METHOD>(P, sh, acc);
 }
@@ -267,11 +323,11 @@ __global__ void __launch_bounds__(kLinThreads, MINB) correspond_kernel(const Lin
     Pose32 pose;
     if (threadIdx.x == 0) sq_len = 0;
     if (!load_pose(P, sh, pose)) return;                         // loop already finished: nothing to do
-    correspond_pass<METHOD>(P, pose, sq, &sq_len);
+    correspond_pass<METHOD, true>(P, pose, sq, &sq_len);
 }
 
 template <int METHOD>
-__global__ void __launch_bounds__(kLinThreads, 3) accumulate_kernel(const LinParams P) {
+__global__ void __launch_bounds__(kLinThreads, kAccMinBlocks) accumulate_kernel(const LinParams P) {
     __shared__ BlockShared sh;
     Pose32 pose;
     if (!load_pose(P, sh, pose)) return;
@@ -287,7 +343,7 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_fused_kernel(cons
     Pose32 pose;
     if (threadIdx.x == 0) sq_len = 0;
     if (!load_pose(P, sh, pose)) return;
-    correspond_pass<METHOD>(P, pose, sq, &sq_len);
+    correspond_pass<METHOD, false>(P, pose, sq, &sq_len);
     __syncthreads();                                             // queue results were parked by other threads of this block
     accumulate_pass<METHOD>(P, sh, pose);
 }
@@ -325,7 +381,7 @@ __global__ void gn_step_kernel(LoopState* st, double tol, int max_iter) {
 struct T16 { double v[16]; };
 __global__ void loop_init_kernel(LoopState* st, T16 T0) {
     if (threadIdx.x < 16) st->T[threadIdx.x] = T0.v[threadIdx.x];
-    if (threadIdx.x == 0) { st->iter = 0; st->done = 0; st->ticket = 0u; st->dx_norm = 0.0; }
+    if (threadIdx.x == 0) { st->iter = 0; st->done = 0; st->ticket = 0u; st->next_row = 0; st->dx_norm = 0.0; }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -520,6 +576,7 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.shell = ctx->tgt_shell;
     P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
     P.use_queue = ctx->use_queue;
+    P.grab_rows = ctx->grab_rows;
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
     const float md = (float)max_dist;
     P.max_d2 = md * md;

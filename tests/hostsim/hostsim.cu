@@ -42,9 +42,9 @@ void* hs_grid_build(const float* xyz, int64_t n, double h) {
         }
     GridView& V = g->v;
     V.h = (float)h; V.inv_h = (float)(1.0 / h);
-    V.ox = lo[0] - 0.25f * V.h; V.oy = lo[1] - 0.25f * V.h; V.oz = lo[2] - 0.25f * V.h;
+    V.ox = lo[0] - 2.25f * V.h; V.oy = lo[1] - 2.25f * V.h; V.oz = lo[2] - 2.25f * V.h;
     double c[3];
-    for (int a = 0; a < 3; ++a) c[a] = floor(((double)hi[a] - (double)(lo[a] - 0.25f * V.h)) / h) + 2.0;
+    for (int a = 0; a < 3; ++a) c[a] = floor(((double)hi[a] - (double)(lo[a] - 2.25f * V.h)) / h) + 4.0;
     V.bnx = (int)(c[0] / 4.0 + 1.0); V.bny = (int)(c[1] / 4.0 + 1.0); V.bnz = (int)(c[2] / 4.0 + 1.0);
     V.cnx = V.bnx * 4; V.cny = V.bny * 4; V.cnz = V.bnz * 4;
     V.slack = 1e-3f + 1e-6f * (float)(2.0 * maxabs / h + (double)std::max(V.cnx, std::max(V.cny, V.cnz)));
@@ -128,7 +128,9 @@ int64_t hs_shell_build(void* gp, double dmax_frac) {
         {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
         {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}, {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1},
         {-1, -1, -1}, {1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}, {1, 1, 1}};
-    static const float frac[PCR_SHELL_LEVELS] = {0.0f, 0.03125f, 0.0625f, 0.125f, 0.1768f, 0.25f, 0.3536f, 0.5f, 0.7071f, 1.0f, 1.4142f, 2.0f};
+    static const float frac[PCR_SHELL_LEVELS] = {
+        0.0f, 0.0442f, 0.0526f, 0.0625f, 0.0743f, 0.0884f, 0.1051f, 0.125f, 0.1487f, 0.1768f, 0.2102f, 0.25f,
+        0.2973f, 0.3536f, 0.4204f, 0.5f, 0.5946f, 0.7071f, 0.8409f, 1.0f, 1.1892f, 1.4142f, 1.6818f, 2.0f};
     const int R = dmax_frac <= 1.0 ? 1 : 2;
     const int side = 2 * R + 1, ncell = side * side * side, centre = (ncell - 1) / 2;
     const float dmax = (float)(dmax_frac * (double)G.h);
@@ -187,18 +189,25 @@ int64_t hs_shell_build(void* gp, double dmax_frac) {
             }
             const uint32_t base = (uint32_t)g->shell_pts.size();
             g->shell_start.push_back(base);
-            uint32_t total = 0;
+            std::vector<float4> flat;
+            std::vector<float> bounds;
             for (int l = 0; l < PCR_SHELL_LEVELS; ++l) {
                 for (size_t k = 0; k < lv[l].size(); ++k) {
-                    if ((total & 3u) == 0u) {
+                    if ((flat.size() & 3u) == 0u) {
                         const float lb = l >= 1 ? fmaxf(frac[l - 1] * G.h - slack_w, 0.0f) : 0.0f;
-                        g->shell_margin2.push_back(lb * lb);
+                        bounds.push_back(lb * lb);
                     }
-                    g->shell_pts.push_back(lv[l][k]);
-                    ++total;
+                    flat.push_back(lv[l][k]);
                 }
             }
-            while (total & 3u) { g->shell_pts.push_back(make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f)); ++total; }
+            while (flat.size() & 3u) flat.push_back(make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f));
+            for (size_t g4 = 0; g4 < flat.size(); g4 += 4) {      // groups of four, structure of arrays
+                g->shell_pts.push_back(make_float4(flat[g4].x, flat[g4 + 1].x, flat[g4 + 2].x, flat[g4 + 3].x));
+                g->shell_pts.push_back(make_float4(flat[g4].y, flat[g4 + 1].y, flat[g4 + 2].y, flat[g4 + 3].y));
+                g->shell_pts.push_back(make_float4(flat[g4].z, flat[g4 + 1].z, flat[g4 + 2].z, flat[g4 + 3].z));
+                g->shell_pts.push_back(make_float4(flat[g4].w, flat[g4 + 1].w, flat[g4 + 2].w, flat[g4 + 3].w));
+            }
+            for (float b2 : bounds) g->shell_margin2.push_back(b2);
             ++ord;
         }
     }
@@ -262,10 +271,13 @@ void hs_shell_study(void* gp, const float* q, int64_t m, double max_dist, double
             for (; k < e; k += 4) {
                 if (S.margin2[k >> 2] >= best) break;
                 ++groups;
-                for (int u = 0; u < 4; ++u) {
-                    const float4 t = S.pts[k + u];
-                    const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz, d = ex * ex + ey * ey + ez * ez;
-                    if (d < best) best = d;
+                {
+                    const float4 X = S.pts[k], Y = S.pts[k + 1], Z = S.pts[k + 2];
+                    const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
+                    for (int u = 0; u < 4; ++u) {
+                        const float d = dist2_rn(xs[u] - qx, ys[u] - qy, zs[u] - qz);
+                        if (d < best) best = d;
+                    }
                 }
             }
             if (k >= e && !(best <= S.covered2)) out[2] += 1;
