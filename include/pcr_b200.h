@@ -106,6 +106,12 @@ int pcr_get_voxels(pcr_ctx* ctx, double* mean, double* cov, double* norm, double
  * context's stream, every later call is ordered behind it).  Replaces
  * `source.astype(np.float32)` (registration.py:83). */
 int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort);
+/* Same, with the pose the iteration will start from and the method (PCR_ICP .. PCR_NDT, or -1)
+ * whose correspondence grid is meant: with sort > 0 the scan is ordered by the grid cell its posed
+ * points fall into, so that the 32 slots of a warp row share one or two candidate lists (a rigid
+ * motion keeps that order coherent over the iterations).  Falls back to the Morton order of
+ * pcr_set_scan when the grid does not exist yet.  T = NULL means identity. */
+int pcr_set_scan_posed(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, const double T[16], int method);
 
 /* ---- per iteration --------------------------------------------------------------------- */
 

@@ -38,6 +38,7 @@ SYMBOLS = {
     "pcr_get_voxel_count": (_i, [_vp, _pi64, _pi64]),
     "pcr_get_voxels": (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "pcr_set_scan": (_i, [_vp, _vp, _i64, _i]),
+    "pcr_set_scan_posed": (_i, [_vp, _vp, _i64, _i, _vp, _i]),
     "pcr_linearize": (_i, [_vp, _i, _vp, _d, _vp]),
     "pcr_align": (_i, [_vp, _i, _vp, _i, _d, _d, _vp, _pi, _vp]),
     "pcr_loop_begin": (_i, [_vp, _vp]),
@@ -234,10 +235,12 @@ class Context:
         return mean, cov, norm, icov, count
 
     # -- scan side ------------------------------------------------------------------------
-    def set_scan(self, pts_f32, sort=True):
-        """sort: True/1 Morton-sort on the device; False/0 keep order (per-point search);
-        -1 keep order, caller promises spatial coherence."""
-        self._check(self._lib.pcr_set_scan(self._h, _ptr(pts_f32), pts_f32.shape[0], int(sort)))
+    def set_scan(self, pts_f32, sort=True, T=None, method=-1):
+        """sort: True/1 re-order on the device (by the correspondence-grid cell of the points posed
+        by T when that grid exists, else along a Morton curve); False/0 keep order; -1 keep order,
+        caller promises spatial coherence."""
+        Tp = None if T is None else np.ascontiguousarray(T, dtype=np.float64)
+        self._check(self._lib.pcr_set_scan_posed(self._h, _ptr(pts_f32), pts_f32.shape[0], int(sort), _ptr(Tp), int(method)))
 
     def set_voxel_lists(self, enable):
         self._check(self._lib.pcr_set_voxel_lists(self._h, int(bool(enable))))

@@ -83,7 +83,8 @@ struct pcr_ctx {
     pcr::ShellLists tgt_shell{};  // null pointers = not built
     long long n_shell_band = 0, n_shell_entries = 0;
     int use_shell_lists = 1;
-    int use_queue = 1;            // linearise kernel: list misses go to the block queue (0: searched in place, A/B)
+    int use_queue = 0;            // 1: list misses go to a block queue worked off at the end of the block (measured slower
+                                  // once rows are scheduled dynamically: the queue serialises the stragglers into a tail)
     double shell_dmax_frac = 2.0; // requested list margin in cell edges (<= 2); reduced until the lists fit shell_max_gib
     double shell_max_gib = 24.0;  // memory cap of the lists
     double shell_dmax_used = 0.0; // margin actually built (0: no lists)
@@ -110,7 +111,8 @@ struct pcr_ctx {
     bool scan_sorted = false;     // spatially coherent order (Morton-sorted on upload, or promised by the caller)
     double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
     int min_blocks = 4;           // resident blocks per SM requested for the correspondence pass (3..6)
-    int grab_rows = 1;            // rows of 32 scan slots a warp fetches at a time
+    int cell_order = 1;           // scan upload: order by correspondence-grid cell (0: Morton order in the scan's frame)
+    int grab_rows = 0;            // rows of 32 scan slots a warp fetches at a time (0: chosen from the scan size)
     int split_passes = 1;         // 1: correspond + accumulate kernels, 0: one fused kernel (A/B)
     int lin_blocks_per_sm[4][9] = {};   // cached occupancy per (method, kernel variant)
     pcr::DevBuf scan_x, scan_y, scan_z;

@@ -418,6 +418,30 @@ __global__ void morton_key_kernel(const float* __restrict__ xyz, long long n, co
     vals[i] = (uint32_t)i;
 }
 
+// Sort key of a scan point = the cell of the correspondence grid its image under the given pose
+// falls into (brick-major, as the grid itself is ordered): the 32 slots of a warp row then sit in
+// one or two cells and stream the SAME list, instead of 4-8 cells with a Morton order in the
+// scan's own frame.  A rigid motion moves the points of one cell together, so the order stays
+// coherent over the Gauss-Newton iterations.
+__global__ void cell_key_kernel(const float* __restrict__ xyz, long long n, GridView G, Pose32 pose,
+                                unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float qx, qy, qz;
+    transform32(pose, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], qx, qy, qz);
+    const float big = 1.0e9f;
+    float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
+    if (!(gx == gx)) gx = 0.f;
+    if (!(gy == gy)) gy = 0.f;
+    if (!(gz == gz)) gz = 0.f;
+    const int cx = cell_of(fminf(fmaxf(gx, -big), big), G.cnx);
+    const int cy = cell_of(fminf(fmaxf(gy, -big), big), G.cny);
+    const int cz = cell_of(fminf(fmaxf(gz, -big), big), G.cnz);
+    const unsigned long long brick = ((unsigned long long)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2);
+    keys[i] = brick * 64ull + (unsigned long long)brick_bit(cx, cy, cz);
+    vals[i] = (uint32_t)i;
+}
+
 __global__ void scan_to_soa_kernel(const float* __restrict__ xyz, const uint32_t* __restrict__ order, long long n, long long n_pad,
                                    float* __restrict__ sx, float* __restrict__ sy, float* __restrict__ sz) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -576,7 +600,13 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.shell = ctx->tgt_shell;
     P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
     P.use_queue = ctx->use_queue;
-    P.grab_rows = ctx->grab_rows;
+    // rows per fetch: about 16 fetches per resident warp (one device-wide counter serves them all;
+    // a fetch per row would make it the bottleneck of a 10M-point scan), at least 1
+    {
+        const long long rows = ctx->n_scan_pad / 32, warps = (long long)ctx->sm_count * ctx->min_blocks * (kLinThreads / 32);
+        long long per = ctx->grab_rows > 0 ? ctx->grab_rows : rows / (warps * 16);
+        P.grab_rows = (int)(per < 1 ? 1 : (per > 64 ? 64 : per));
+    }
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
     const float md = (float)max_dist;
     P.max_d2 = md * md;
@@ -646,7 +676,13 @@ using namespace pcr;
 
 extern "C" {
 
-int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
+static int bits_for_u64(unsigned long long v) {   // number of bits needed to represent values < v
+    int b = 0;
+    while (b < 64 && (1ull << b) < v) ++b;
+    return b < 1 ? 1 : b;
+}
+
+static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, const double* T, int method) {
     if (!ctx) return PCR_ERR_ARG;
     if (n < 0 || (n > 0 && !xyz)) return fail(ctx, PCR_ERR_ARG, "pcr_set_scan: bad arguments");
     if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "pcr_set_scan: point count exceeds 2^31-1");
@@ -672,28 +708,57 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
     PCR_CUDA(ctx->scan_y.ensure(pad_bytes));
     PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
     PCR_CUDA(ctx->scan_prev.ensure(pad_bytes));
-    ctx->prev_which = -1;                       // new scan: no warm start
+    ctx->prev_which = -1;                       // new scan: parked positions are void
     const uint32_t* order = nullptr;
     if (sort > 0 && n > 1) {
-        PCR_CUDA(ctx->tmp_e.ensure(64));
-        int* d_mm = ctx->tmp_e.as<int>();
-        mm_init_kernel<<<1, 32, 0, ctx->stream>>>(d_mm);
-        PCR_LAUNCH_CHECK();
-        int nb = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
-        scan_bbox_kernel<<<nb, 256, 0, ctx->stream>>>(d_xyz, n, d_mm);
-        PCR_LAUNCH_CHECK();
-        PCR_CUDA(ctx->tmp_c.ensure((size_t)n * 4 * 2));
-        PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
-        uint32_t* k_in = ctx->tmp_c.as<uint32_t>(); uint32_t* k_out = k_in + n;
-        uint32_t* v_in = ctx->tmp_d.as<uint32_t>(); uint32_t* v_out = v_in + n;
-        morton_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, d_mm, k_in, v_in);
-        PCR_LAUNCH_CHECK();
-        size_t tmp = 0;
-        PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
-        PCR_CUDA(ctx->cub_tmp.ensure(tmp));
-        PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
-        ctx->launches += 4;
-        order = v_out;
+        // the grid the correspondences will be searched in, if it exists already
+        const Grid* g = nullptr;
+        if ((method == PCR_VPLANE || method == PCR_NDT) && ctx->vox_grid.built && ctx->vox_grid.view.n_pts > 0) g = &ctx->vox_grid;
+        else if ((method == PCR_ICP || method == PCR_PLANE || method < 0) && ctx->tgt_grid.built) g = &ctx->tgt_grid;
+        else if (method < 0 && ctx->vox_grid.built && ctx->vox_grid.view.n_pts > 0) g = &ctx->vox_grid;
+        if (g && ctx->cell_order) {
+            // order by the grid cell of the posed point (see cell_key_kernel)
+            const double I[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+            Pose32 pose;
+            pose32_from_T(T ? T : I, pose);
+            PCR_CUDA(ctx->tmp_a.ensure((size_t)n * 8));
+            PCR_CUDA(ctx->tmp_b.ensure((size_t)n * 8));
+            PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
+            unsigned long long* k_in = ctx->tmp_a.as<unsigned long long>();
+            unsigned long long* k_out = ctx->tmp_b.as<unsigned long long>();
+            uint32_t* v_in = ctx->tmp_d.as<uint32_t>(); uint32_t* v_out = v_in + n;
+            cell_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, g->view, pose, k_in, v_in);
+            PCR_LAUNCH_CHECK();
+            const unsigned long long nkeys = (unsigned long long)g->view.bnx * g->view.bny * g->view.bnz * 64ull;
+            const int end_bit = bits_for_u64(nkeys);
+            size_t tmp = 0;
+            PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
+            PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+            PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
+            ctx->launches += 4;
+            order = v_out;
+        } else {
+            // no grid yet: Morton order in the scan's own bounding box
+            PCR_CUDA(ctx->tmp_e.ensure(64));
+            int* d_mm = ctx->tmp_e.as<int>();
+            mm_init_kernel<<<1, 32, 0, ctx->stream>>>(d_mm);
+            PCR_LAUNCH_CHECK();
+            int nb = (int)std::min<long long>((n + 255) / 256, (long long)ctx->sm_count * 8);
+            scan_bbox_kernel<<<nb, 256, 0, ctx->stream>>>(d_xyz, n, d_mm);
+            PCR_LAUNCH_CHECK();
+            PCR_CUDA(ctx->tmp_c.ensure((size_t)n * 4 * 2));
+            PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
+            uint32_t* k_in = ctx->tmp_c.as<uint32_t>(); uint32_t* k_out = k_in + n;
+            uint32_t* v_in = ctx->tmp_d.as<uint32_t>(); uint32_t* v_out = v_in + n;
+            morton_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, d_mm, k_in, v_in);
+            PCR_LAUNCH_CHECK();
+            size_t tmp = 0;
+            PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
+            PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+            PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, 30, ctx->stream));
+            ctx->launches += 4;
+            order = v_out;
+        }
         ctx->scan_sorted = true;
     }
     if (sort < 0) ctx->scan_sorted = true;      // caller promises a spatially coherent order
@@ -707,6 +772,12 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) {
     if (from_host) PCR_CUDA(cudaEventSynchronize(ctx->ev_copy));
     else PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     return PCR_OK;
+}
+
+int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort) { return set_scan_impl(ctx, xyz, n, sort, nullptr, -1); }
+
+int pcr_set_scan_posed(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, const double T[16], int method) {
+    return set_scan_impl(ctx, xyz, n, sort, T, method);
 }
 
 int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max_dist, int reps) {

@@ -50,7 +50,7 @@ class Registration:
         if not self._is_target_set:
             raise ValueError("Target is not set.")
         if not isinstance(source, UploadedScan):
-            self._upload(source, sort=self.sort_scan_on_calc)
+            self._upload(source, sort=self.sort_scan_on_calc, T=cur_T)
         elif source.owner is not self:
             raise ValueError("scan handle belongs to another registration object")
         rec = self._ctx.linearize(self.method, np.asarray(cur_T, dtype=np.float64), self.max_dist)
@@ -60,11 +60,11 @@ class Registration:
     def align(self, source, init_T=np.eye(4), verbose=False, device_loop=None):
         if self.is_target_set() is False:
             raise ValueError("Target is not set.")
+        cur_T = np.asarray(init_T, dtype=np.float64)
         if not isinstance(source, UploadedScan):
-            source = self.upload_scan(source)
+            source = self.upload_scan(source, T=cur_T)
         elif source.owner is not self:
             raise ValueError("scan handle belongs to another registration object")
-        cur_T = np.asarray(init_T, dtype=np.float64)
         if device_loop is None:
             device_loop = not verbose
         if device_loop:
@@ -88,13 +88,14 @@ class Registration:
         return cur_T
 
     # -- extensions ---------------------------------------------------------------------
-    def upload_scan(self, source, sort=None):
+    def upload_scan(self, source, sort=None, T=None):
         """Upload a scan once and get a handle usable with calc_H_g_e2 / align (avoids the
-        per-call host->device copy the array form implies)."""
-        self._upload(source, sort=self.sort_scan if sort is None else sort)
+        per-call host->device copy the array form implies).  ``T``: the pose the iterations will
+        start from (default identity); it only steers the on-device ordering of the scan."""
+        self._upload(source, sort=self.sort_scan if sort is None else sort, T=T)
         return UploadedScan(self)
 
-    def _upload(self, source, sort):
+    def _upload(self, source, sort, T=None):
         if self._ctx is None:
             raise ValueError("Target is not set.")
         src = _lib.as_f32_points(source, "source")               # registration.py:83
@@ -102,7 +103,7 @@ class Registration:
             from .distributed import shard_bounds
             lo, hi = shard_bounds(src.shape[0], *self._dist)
             src = src[lo:hi]
-        self._ctx.set_scan(src, sort=sort)
+        self._ctx.set_scan(src, sort=sort, T=T, method=self.method)
 
     def attach_communicator(self, rank, world_size, unique_id):
         """Multi-GPU: this process owns one GPU and one contiguous tile of every scan; the
