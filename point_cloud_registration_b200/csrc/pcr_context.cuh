@@ -23,7 +23,6 @@ constexpr int kLinThreads = 256;        // threads per block of the linearise ke
 constexpr int kMaxLinBlocks = 148 * 8;  // upper bound on persistent grid size (partials buffer)
 constexpr int kAccBatch = PCR_ACC_BATCH;     // scan slots whose gathers are in flight together in the accumulate pass
 constexpr int kAccMinBlocks = PCR_ACC_MINB;  // resident blocks per SM requested for the accumulate kernel
-constexpr int kQueueCap = 6144;         // per-block straggler queue of the linearise kernel (24 KB of shared memory)
 
 // Device-resident Gauss-Newton loop state (one per context).
 struct LoopState {
@@ -83,8 +82,7 @@ struct pcr_ctx {
     pcr::ShellLists tgt_shell{};  // null pointers = not built
     long long n_shell_band = 0, n_shell_entries = 0;
     int use_shell_lists = 1;
-    int use_queue = 0;            // 1: list misses go to a block queue worked off at the end of the block (measured slower
-                                  // once rows are scheduled dynamically: the queue serialises the stragglers into a tail)
+    int pair_rows = 1;            // correspondence pass: a lane streams the shell lists of two scan slots together
     double shell_dmax_frac = 2.0; // requested list margin in cell edges (<= 2); reduced until the lists fit shell_max_gib
     double shell_max_gib = 24.0;  // memory cap of the lists
     double shell_dmax_used = 0.0; // margin actually built (0: no lists)

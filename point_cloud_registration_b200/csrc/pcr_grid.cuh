@@ -266,43 +266,54 @@ PCR_HD void shell_eval_group(const float4& X, const float4& Y, const float4& Z, 
     }
 }
 
-// Stream the shell list (see ShellLists) of the query's cell.  Returns
-//   0  the cell has no list: nothing was looked at, the caller must run the general search;
-//   1  final: out_d2 / out_pos hold the exact nearest neighbour (or -1: none within max_dist);
-//   2  list exhausted while the best is still beyond the covered margin: out_* hold an upper
-//      bound and the general search has to finish the job.
-PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
+// Cursor over the shell list (see ShellLists) of one query's cell.
+struct ShellCursor {
+    uint32_t k;                // list offset of the next group (entries; multiple of 4)
+    uint32_t e;                // end of the list
+    float m;                   // margin bound of the next group (already loaded)
+    float best;                // best squared distance so far (starts at max_dist^2, strict <)
+    uint32_t best_k;           // list offset of the best entry, 0xffffffff = none
+    bool active;               // more groups to evaluate
+    bool exhausted;            // the list ended (or will end) without a margin bound stopping the scan
+};
+
+// Open the list of the query's cell.  false: the cell has no list (nothing was looked at).
+PCR_HD bool shell_open(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, ShellCursor& c) {
+    c.active = false; c.exhausted = true; c.best = max_d2; c.best_k = 0xffffffffu;
     const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
-    if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) return 0;
+    if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) return false;
     const int cx = (int)gx, cy = (int)gy, cz = (int)gz;
     const uint4 rec = S.bricks[((size_t)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2)];
     const unsigned long long band = ((unsigned long long)rec.y << 32) | rec.x;
     const int bit = brick_bit(cx, cy, cz);
-    if (!((band >> bit) & 1ull)) return 0;
+    if (!((band >> bit) & 1ull)) return false;
     const uint32_t ord = rec.z + (uint32_t)popc64(band & ((1ull << bit) - 1ull));
     const uint32_t s = S.start[ord], e = S.start[ord + 1];
-    float best = max_d2;
-    uint32_t best_k = 0xffffffffu;                            // list offset of the best entry
-    bool exhausted = true;
-    // One group per trip: margin bound of the NEXT group is requested together with the three
-    // vectors of this one (reading one bound past the end is safe and never used).  Deeper software
-    // pipelining was measured: no gain -- the loads hit L1 and other warps cover their latency.
-    const float4* p = S.pts + s;
-    const float4* const pe = S.pts + e;
-    const float* mp = S.margin2 + (s >> 2);
-    float m = mp[0];
-    while (p < pe) {
-        if (m >= best) { exhausted = false; break; }          // everything from here on is at least this far
-        const float4 X = p[0], Y = p[1], Z = p[2];
-        m = mp[1];
-        shell_eval_group(X, Y, Z, qx, qy, qz, (uint32_t)(p - S.pts), best, best_k);
-        p += 4; ++mp;
+    c.k = s; c.e = e;
+    c.m = S.margin2[s >> 2];                                  // (one bound past the end of the array is allocated)
+    if (s < e) {
+        if (c.m >= c.best) c.exhausted = false;               // not even the first group can hold a match
+        else c.active = true;
     }
-    out_d2 = best;
+    return true;
+}
+
+// Advance an active cursor past the group just evaluated; termination tests.
+PCR_HD void shell_advance(ShellCursor& c, float m_next) {
+    c.k += 4; c.m = m_next;
+    if (!(c.k < c.e)) c.active = false;                       // list ended
+    else if (c.m >= c.best) { c.active = false; c.exhausted = false; }   // everything from here on is at least this far
+}
+
+// Result of a finished cursor: 1 = final (out_pos = position in GridView::pts or -1: none within
+// max_dist), 2 = the list ended while the best is still beyond the covered margin: out_* hold an
+// upper bound and the general search has to finish the job.
+PCR_HD int shell_close(const ShellLists& S, const ShellCursor& c, float& out_d2, int& out_pos) {
+    out_d2 = c.best;
     out_pos = -1;
-    if (best_k != 0xffffffffu) {
-        const float4 W = S.pts[(best_k & ~3u) + 3u];
-        const uint32_t j = best_k & 3u;
+    if (c.best_k != 0xffffffffu) {
+        const float4 W = S.pts[(c.best_k & ~3u) + 3u];
+        const uint32_t j = c.best_k & 3u;
         const float w = j == 0u ? W.x : (j == 1u ? W.y : (j == 2u ? W.z : W.w));
 #if defined(__CUDA_ARCH__)
         out_pos = __float_as_int(w);
@@ -310,9 +321,51 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
         memcpy(&out_pos, &w, 4);
 #endif
     }
-    // stopped by a margin bound: final.  List exhausted: final only if the best (or, with no
-    // candidate, the search radius) lies within the covered margin.
-    return (exhausted && !(best <= S.covered2)) ? 2 : 1;
+    return (c.exhausted && !(c.best <= S.covered2)) ? 2 : 1;
+}
+
+// Stream the shell list of ONE query's cell: 0 = no list, else see shell_close.
+PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
+    ShellCursor c;
+    if (!shell_open(G, S, qx, qy, qz, max_d2, c)) return 0;
+    while (c.active) {
+        const float4* g4 = S.pts + c.k;
+        const float4 X = g4[0], Y = g4[1], Z = g4[2];
+        const float mn = S.margin2[(c.k >> 2) + 1];
+        shell_eval_group(X, Y, Z, qx, qy, qz, c.k, c.best, c.best_k);
+        shell_advance(c, mn);
+    }
+    return shell_close(S, c, out_d2, out_pos);
+}
+
+// Stream the lists of TWO queries together: the loads of both cursors are requested before either
+// group is evaluated, which doubles the memory-level parallelism of a lane (the list stream is
+// latency bound: a chain of dependent loads per query).  Statuses as shell_scan.
+PCR_HD void shell_scan_pair(const GridView& G, const ShellLists& S, float ax, float ay, float az, float bx, float by, float bz, float max_d2,
+                            int& sta, float& a_d2, int& a_pos, int& stb, float& b_d2, int& b_pos) {
+    ShellCursor a, b;
+    const bool oa = shell_open(G, S, ax, ay, az, max_d2, a);
+    const bool ob = shell_open(G, S, bx, by, bz, max_d2, b);
+    if (!oa) { a.k = 0u; a.e = 0u; }                            // a closed cursor still points at readable memory
+    if (!ob) { b.k = 0u; b.e = 0u; }
+    while (a.active | b.active) {
+        // Both cursors load AND evaluate unconditionally -- one basic block, six independent vector
+        // loads in flight before the first use.  A finished cursor re-evaluates the group it stopped
+        // at, which cannot change its result: that group was evaluated before, or its margin bound is
+        // >= the best, or it lies behind the end of the list (a real point of another list can only be
+        // accepted if it is closer than everything the finished scan already proved to be nearest).
+        const float4* ga = S.pts + a.k;
+        const float4* gb = S.pts + b.k;
+        const float4 XA = ga[0], YA = ga[1], ZA = ga[2];
+        const float4 XB = gb[0], YB = gb[1], ZB = gb[2];
+        const float ma = S.margin2[(a.k >> 2) + 1], mb = S.margin2[(b.k >> 2) + 1];
+        shell_eval_group(XA, YA, ZA, ax, ay, az, a.k, a.best, a.best_k);
+        shell_eval_group(XB, YB, ZB, bx, by, bz, b.k, b.best, b.best_k);
+        if (a.active) shell_advance(a, ma);
+        if (b.active) shell_advance(b, mb);
+    }
+    sta = oa ? shell_close(S, a, a_d2, a_pos) : 0;
+    stb = ob ? shell_close(S, b, b_d2, b_pos) : 0;
 }
 
 // 1-NN through the shell lists with the general search as continuation (host replay, and the

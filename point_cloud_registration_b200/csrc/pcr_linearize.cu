@@ -2,9 +2,9 @@
 //
 //   correspond   coalesced loads of the SoA scan -> SE(3) transform (float32) -> exact nearest
 //                neighbour: every query streams the list of its cell (voxel means: exact candidate
-//                list; target points: margin-ordered shell list); the few queries a list cannot
-//                settle go to a block queue and are searched in the brick grid with all lanes
-//                busy -> matched position parked per scan slot (4 B/point)
+//                list; target points: margin-ordered shell list, two slots per lane in flight);
+//                the few queries a list cannot settle are searched in the brick grid
+//                -> matched position parked per scan slot (4 B/point)
 //   accumulate   gather the matched record -> residual + 6-DoF Jacobian terms -> per-thread float32
 //                sums -> float64 warp shuffles + shared-memory block reduction -> per-block partial
 //                -> the LAST block to arrive sums the partials in a fixed order (deterministic),
@@ -38,7 +38,7 @@ struct LinParams {
     ShellLists shell;                                    // ICP/PLANE: per-cell shell lists (null = absent)
     int use_shell;
     int grab_rows;                                       // rows of 32 scan slots a warp fetches at a time (correspondence pass)
-    int use_queue;                                       // park list misses in the block queue (pass 1b) instead of searching in place
+    int pair_rows;                                       // target-point lists: a lane streams the lists of two slots together
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
     double T_param[16];
@@ -193,7 +193,8 @@ __device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, P
 
 // The general brick-grid search as an out-of-line call: it only serves stragglers, and inlined it
 // would set the register budget (and so the occupancy) of the list-streaming loop around it.
-__device__ __noinline__ int general_nn(const GridView& G, float qx, float qy, float qz, float max_d2) {
+__device__ __noinline__ int general_nn(const GridView G, float qx, float qy, float qz, float max_d2) {   // by value: the kernel
+    // parameter block stays in the constant bank instead of being copied to local memory for its address
     float d2;
     return grid_nn(G, qx, qy, qz, max_d2, d2);
 }
@@ -204,41 +205,39 @@ __device__ __noinline__ int general_nn(const GridView& G, float qx, float qy, fl
 // or the best still beyond the listed margin) are NOT searched here, where they would stall the
 // other 31 lanes of their warp: their scan slots go to a block queue.  1b: the block works the
 // queue off with every lane busy (general brick-grid search).
-// one scan slot: list stream, or a ticket in the block queue
+// one scan slot: list stream; the general search for what no list can settle
 template <int METHOD>
-__device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32& pose, int* sq, int* sq_len, long long i, int lane, bool lists) {
+__device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32& pose, long long i, bool lists) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
     const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
-    float qx, qy, qz;
-    transform32(pose, px, py, pz, qx, qy, qz);
-    float d2;
     int pos = -1;
-    bool pending = false;
-    if (lists) {
-        if (px == px) {                                          // NaN = padding: no match
-            if (kVoxel) pending = !list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
-            else pending = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) != 1;
+    if (px == px) {                                              // NaN = padding: no match
+        float qx, qy, qz, d2;
+        transform32(pose, px, py, pz, qx, qy, qz);
+        bool settled = false;
+        if (lists) {
+            if (kVoxel) settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
+            else settled = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) == 1;
         }
-        if (P.use_queue) {
-            const unsigned m = __ballot_sync(0xffffffffu, pending);
-            if (m) {
-                const int leader = __ffs(m) - 1;
-                int base = 0;
-                if (lane == leader) base = atomicAdd(sq_len, __popc(m));
-                base = __shfl_sync(0xffffffffu, base, leader);
-                if (pending) {
-                    const int slot = base + __popc(m & ((1u << lane) - 1u));
-                    if (slot < kQueueCap) sq[slot] = (int)i;
-                    else pos = general_nn(P.grid, qx, qy, qz, P.max_d2);           // queue full: search in place
-                }
-            }
-        } else if (pending) {
-            pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
-        }
-    } else if (px == px) {
-        pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
+        if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
     }
     P.prev[i] = pos;
+}
+
+// two scan slots of one lane at once (target-point methods): both list streams in flight together
+__device__ __forceinline__ void correspond_slot_pair(const LinParams& P, const Pose32& pose, long long ia, long long ib) {
+    const float ax = __ldg(P.sx + ia), ay = __ldg(P.sy + ia), az = __ldg(P.sz + ia);
+    const float bx = __ldg(P.sx + ib), by = __ldg(P.sy + ib), bz = __ldg(P.sz + ib);
+    float qax, qay, qaz, qbx, qby, qbz;                          // NaN padding stays NaN: shell_open rejects it
+    transform32(pose, ax, ay, az, qax, qay, qaz);
+    transform32(pose, bx, by, bz, qbx, qby, qbz);
+    int sta, stb, pa, pb;
+    float da, db;
+    shell_scan_pair(P.grid, P.shell, qax, qay, qaz, qbx, qby, qbz, P.max_d2, sta, da, pa, stb, db, pb);
+    if (sta != 1) pa = ax == ax ? general_nn(P.grid, qax, qay, qaz, P.max_d2) : -1;
+    if (stb != 1) pb = bx == bx ? general_nn(P.grid, qbx, qby, qbz, P.max_d2) : -1;
+    P.prev[ia] = pa;
+    P.prev[ib] = pb;
 }
 
 // DYNAMIC: warps fetch rows of 32 consecutive scan slots from a device-wide counter (P.grab_rows
@@ -246,37 +245,31 @@ __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32
 // the slowest SM 30 % behind the average.  The parked result of a slot does not depend on who
 // computed it and the accumulate pass keeps its fixed order, so results stay deterministic.  Only
 // possible when the accumulate pass is a separate kernel (it reads slots parked by other blocks).
+// (A block-level queue that collected the list misses and searched them at the end of the block
+// was measured and removed: with dynamic rows it only serialises the stragglers into a tail.)
 template <int METHOD, bool DYNAMIC>
-__device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32& pose, int* sq, int* sq_len) {
+__device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32& pose) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
     const int lane = threadIdx.x & 31;
     const bool lists = kVoxel ? (P.use_lists != 0) : (P.use_shell != 0);
     if (DYNAMIC) {
         const int rows_total = (int)(P.n_pad >> 5);
+        const bool pairs = !kVoxel && lists && P.pair_rows;
         for (;;) {
             int r0 = 0;
             if (lane == 0) r0 = atomicAdd(&P.st->next_row, P.grab_rows);
             r0 = __shfl_sync(0xffffffffu, r0, 0);
             if (r0 >= rows_total) break;
             const int r1 = r0 + P.grab_rows < rows_total ? r0 + P.grab_rows : rows_total;
-            for (int r = r0; r < r1; ++r) correspond_slot<METHOD>(P, pose, sq, sq_len, ((long long)r << 5) + lane, lane, lists);
+            int r = r0;
+            if (pairs)
+                for (; r + 1 < r1; r += 2) correspond_slot_pair(P, pose, ((long long)r << 5) + lane, ((long long)(r + 1) << 5) + lane);
+            for (; r < r1; ++r) correspond_slot<METHOD>(P, pose, ((long long)r << 5) + lane, lists);
         }
     } else {
-        const long long stride = (long long)gridDim.x * kLinThreads;   // n_pad and stride are multiples of 32: warps stay whole
+        const long long stride = (long long)gridDim.x * kLinThreads;
         for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride)
-            correspond_slot<METHOD>(P, pose, sq, sq_len, i, lane, lists);
-    }
-    __syncthreads();
-    // queue item k goes to lane k / 8 of warp k % 8 (then round again): a short queue is spread over
-    // all warps of the block, whose searches overlap, instead of filling the lanes of one warp
-    const int nq = *sq_len < kQueueCap ? *sq_len : kQueueCap;
-    constexpr int kWarps = kLinThreads / 32;
-    for (int k = (threadIdx.x & 31) * kWarps + (threadIdx.x >> 5); k < nq; k += kLinThreads) {
-        const long long i = sq[k];
-        const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
-        float qx, qy, qz;
-        transform32(pose, px, py, pz, qx, qy, qz);
-        P.prev[i] = general_nn(P.grid, qx, qy, qz, P.max_d2);
+            correspond_slot<METHOD>(P, pose, i, lists);
     }
 }
 
@@ -318,12 +311,9 @@ __device__ __forceinline__ void accumulate_pass(const LinParams& P, BlockShared&
 template <int METHOD, int MINB>
 __global__ void __launch_bounds__(kLinThreads, MINB) correspond_kernel(const LinParams P) {
     __shared__ BlockShared sh;
-    __shared__ int sq[kQueueCap];
-    __shared__ int sq_len;
     Pose32 pose;
-    if (threadIdx.x == 0) sq_len = 0;
     if (!load_pose(P, sh, pose)) return;                         // loop already finished: nothing to do
-    correspond_pass<METHOD, true>(P, pose, sq, &sq_len);
+    correspond_pass<METHOD, true>(P, pose);
 }
 
 template <int METHOD>
@@ -338,13 +328,9 @@ __global__ void __launch_bounds__(kLinThreads, kAccMinBlocks) accumulate_kernel(
 template <int METHOD, int MINB>
 __global__ void __launch_bounds__(kLinThreads, MINB) linearize_fused_kernel(const LinParams P) {
     __shared__ BlockShared sh;
-    __shared__ int sq[kQueueCap];
-    __shared__ int sq_len;
     Pose32 pose;
-    if (threadIdx.x == 0) sq_len = 0;
     if (!load_pose(P, sh, pose)) return;
-    correspond_pass<METHOD, false>(P, pose, sq, &sq_len);
-    __syncthreads();                                             // queue results were parked by other threads of this block
+    correspond_pass<METHOD, false>(P, pose);
     accumulate_pass<METHOD>(P, sh, pose);
 }
 
@@ -599,12 +585,13 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
     P.shell = ctx->tgt_shell;
     P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
-    P.use_queue = ctx->use_queue;
+    P.pair_rows = ctx->pair_rows;
     // rows per fetch: about 16 fetches per resident warp (one device-wide counter serves them all;
     // a fetch per row would make it the bottleneck of a 10M-point scan), at least 1
     {
         const long long rows = ctx->n_scan_pad / 32, warps = (long long)ctx->sm_count * ctx->min_blocks * (kLinThreads / 32);
         long long per = ctx->grab_rows > 0 ? ctx->grab_rows : rows / (warps * 16);
+        if (ctx->pair_rows && ctx->grab_rows <= 0) per = per < 2 ? 2 : (per + 1) / 2 * 2;   // whole pairs
         P.grab_rows = (int)(per < 1 ? 1 : (per > 64 ? 64 : per));
     }
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();

@@ -224,14 +224,24 @@ int64_t hs_shell_build(void* gp, double dmax_frac) {
 
 // 1-NN through the shell lists (general search when the cell has no list), as the kernel does.
 // used_list[i] = 1 when the list path answered.
-void hs_shell_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, float* dist, uint8_t* used_list) {
+void hs_shell_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, float* dist, uint8_t* used_list, int pair) {
     HostGrid* g = (HostGrid*)gp;
     const GridView& G = g->v;
     const float md = (float)max_dist;
     for (int64_t i = 0; i < m; ++i) {
         float d2;
         int pos;
-        const bool ok = shell_nn(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
+        bool ok;
+        if (pair) {
+            // the kernel's two-at-a-time stream: query i together with query m - 1 - i
+            const int64_t o = m - 1 - i;
+            int sta, stb, pb; float db;
+            shell_scan_pair(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], q[3 * o], q[3 * o + 1], q[3 * o + 2], md * md, sta, d2, pos, stb, db, pb);
+            ok = sta != 0;
+            if (sta == 2) { Best1 b; b.d2 = d2; b.pos = pos; grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], b); d2 = b.d2; pos = b.pos; }
+        } else {
+            ok = shell_nn(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
+        }
         if (!ok) pos = grid_nn(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2);
         if (used_list) used_list[i] = ok ? 1 : 0;
         if (pos >= 0) {

@@ -33,7 +33,7 @@ def hs():
     lib.hs_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
     lib.hs_shell_build.restype = C.c_int64
     lib.hs_shell_build.argtypes = [C.c_void_p, C.c_double]
-    lib.hs_shell_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.hs_shell_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
     lib.hs_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.hs_linearize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_gn_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -153,12 +153,13 @@ def test_shell_lists_match_general_search(hs, dmax_frac):
             q = np.ascontiguousarray(q)
             i0 = np.empty(len(q), np.int64); d0 = np.empty(len(q), np.float32)
             hs.hs_nn(g, ptr(q), len(q), float(md), ptr(i0), ptr(d0))
-            i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32); used = np.zeros(len(q), np.uint8)
-            hs.hs_shell_nn(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1), ptr(used))
-            assert np.array_equal(d0, d1)
-            assert np.array_equal(i0 < 0, i1 < 0) and (i0 == i1).mean() > 0.999
-            if expect_lists:
-                assert used.mean() > 0.5
+            for pair in (0, 1):                               # one query at a time / the kernel's two-at-a-time stream
+                i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32); used = np.zeros(len(q), np.uint8)
+                hs.hs_shell_nn(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1), ptr(used), pair)
+                assert np.array_equal(d0, d1)
+                assert np.array_equal(i0 < 0, i1 < 0) and (i0 == i1).mean() > 0.999
+                if expect_lists:
+                    assert used.mean() > 0.5
         hs.hs_grid_free(g)
 
 
