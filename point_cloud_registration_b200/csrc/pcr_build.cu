@@ -1118,11 +1118,10 @@ int pcr_create(int device_id, pcr_ctx** out) {
         delete ctx;
         return fail(nullptr, PCR_ERR_CUDA, m);
     }
-    if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) >= 3 && atoi(e) <= 6 ? atoi(e) : 4;
+    if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) >= 3 && atoi(e) <= 6 ? atoi(e) : 0;
     if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 24.0;
     if (const char* e = getenv("PCR_SHELL_DMAX")) ctx->shell_dmax_frac = atof(e) > 0.0 && atof(e) <= 2.0 ? atof(e) : 1.0;
     if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 24.0;
-    if (const char* e = getenv("PCR_PAIR_ROWS")) ctx->pair_rows = atoi(e) != 0;
     if (const char* e = getenv("PCR_LIST_DILATE")) ctx->list_dilate = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 3;
     if (const char* e = getenv("PCR_LIST_RADIUS")) ctx->list_radius = atoi(e) >= 2 && atoi(e) <= 6 ? atoi(e) : 5;
     if (const char* e = getenv("PCR_CELL_ORDER")) ctx->cell_order = atoi(e) != 0;

@@ -82,7 +82,6 @@ struct pcr_ctx {
     pcr::ShellLists tgt_shell{};  // null pointers = not built
     long long n_shell_band = 0, n_shell_entries = 0;
     int use_shell_lists = 1;
-    int pair_rows = 1;            // correspondence pass: a lane streams the shell lists of two scan slots together
     double shell_dmax_frac = 2.0; // requested list margin in cell edges (<= 2); reduced until the lists fit shell_max_gib
     double shell_max_gib = 24.0;  // memory cap of the lists
     double shell_dmax_used = 0.0; // margin actually built (0: no lists)
@@ -108,7 +107,7 @@ struct pcr_ctx {
     bool scan_set = false;
     bool scan_sorted = false;     // spatially coherent order (Morton-sorted on upload, or promised by the caller)
     double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
-    int min_blocks = 4;           // resident blocks per SM requested for the correspondence pass (3..6)
+    int min_blocks = 0;           // resident blocks per SM requested for the correspondence pass (3..6; 0: per-method default)
     int cell_order = 1;           // scan upload: order by correspondence-grid cell (0: Morton order in the scan's frame)
     int grab_rows = 0;            // rows of 32 scan slots a warp fetches at a time (0: chosen from the scan size)
     int split_passes = 1;         // 1: correspond + accumulate kernels, 0: one fused kernel (A/B)

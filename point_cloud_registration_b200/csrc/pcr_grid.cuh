@@ -338,36 +338,6 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
     return shell_close(S, c, out_d2, out_pos);
 }
 
-// Stream the lists of TWO queries together: the loads of both cursors are requested before either
-// group is evaluated, which doubles the memory-level parallelism of a lane (the list stream is
-// latency bound: a chain of dependent loads per query).  Statuses as shell_scan.
-PCR_HD void shell_scan_pair(const GridView& G, const ShellLists& S, float ax, float ay, float az, float bx, float by, float bz, float max_d2,
-                            int& sta, float& a_d2, int& a_pos, int& stb, float& b_d2, int& b_pos) {
-    ShellCursor a, b;
-    const bool oa = shell_open(G, S, ax, ay, az, max_d2, a);
-    const bool ob = shell_open(G, S, bx, by, bz, max_d2, b);
-    if (!oa) { a.k = 0u; a.e = 0u; }                            // a closed cursor still points at readable memory
-    if (!ob) { b.k = 0u; b.e = 0u; }
-    while (a.active | b.active) {
-        // Both cursors load AND evaluate unconditionally -- one basic block, six independent vector
-        // loads in flight before the first use.  A finished cursor re-evaluates the group it stopped
-        // at, which cannot change its result: that group was evaluated before, or its margin bound is
-        // >= the best, or it lies behind the end of the list (a real point of another list can only be
-        // accepted if it is closer than everything the finished scan already proved to be nearest).
-        const float4* ga = S.pts + a.k;
-        const float4* gb = S.pts + b.k;
-        const float4 XA = ga[0], YA = ga[1], ZA = ga[2];
-        const float4 XB = gb[0], YB = gb[1], ZB = gb[2];
-        const float ma = S.margin2[(a.k >> 2) + 1], mb = S.margin2[(b.k >> 2) + 1];
-        shell_eval_group(XA, YA, ZA, ax, ay, az, a.k, a.best, a.best_k);
-        shell_eval_group(XB, YB, ZB, bx, by, bz, b.k, b.best, b.best_k);
-        if (a.active) shell_advance(a, ma);
-        if (b.active) shell_advance(b, mb);
-    }
-    sta = oa ? shell_close(S, a, a_d2, a_pos) : 0;
-    stb = ob ? shell_close(S, b, b_d2, b_pos) : 0;
-}
-
 // 1-NN through the shell lists with the general search as continuation (host replay, and the
 // kernels' inline path when the straggler queue is full or disabled).  false: the cell has no list.
 PCR_HD bool shell_nn(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {

@@ -2,7 +2,7 @@
 //
 //   correspond   coalesced loads of the SoA scan -> SE(3) transform (float32) -> exact nearest
 //                neighbour: every query streams the list of its cell (voxel means: exact candidate
-//                list; target points: margin-ordered shell list, two slots per lane in flight);
+//                list; target points: margin-ordered shell list);
 //                the few queries a list cannot settle are searched in the brick grid
 //                -> matched position parked per scan slot (4 B/point)
 //   accumulate   gather the matched record -> residual + 6-DoF Jacobian terms -> per-thread float32
@@ -38,7 +38,6 @@ struct LinParams {
     ShellLists shell;                                    // ICP/PLANE: per-cell shell lists (null = absent)
     int use_shell;
     int grab_rows;                                       // rows of 32 scan slots a warp fetches at a time (correspondence pass)
-    int pair_rows;                                       // target-point lists: a lane streams the lists of two slots together
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
     double T_param[16];
@@ -224,29 +223,14 @@ __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32
     P.prev[i] = pos;
 }
 
-// two scan slots of one lane at once (target-point methods): both list streams in flight together
-__device__ __forceinline__ void correspond_slot_pair(const LinParams& P, const Pose32& pose, long long ia, long long ib) {
-    const float ax = __ldg(P.sx + ia), ay = __ldg(P.sy + ia), az = __ldg(P.sz + ia);
-    const float bx = __ldg(P.sx + ib), by = __ldg(P.sy + ib), bz = __ldg(P.sz + ib);
-    float qax, qay, qaz, qbx, qby, qbz;                          // NaN padding stays NaN: shell_open rejects it
-    transform32(pose, ax, ay, az, qax, qay, qaz);
-    transform32(pose, bx, by, bz, qbx, qby, qbz);
-    int sta, stb, pa, pb;
-    float da, db;
-    shell_scan_pair(P.grid, P.shell, qax, qay, qaz, qbx, qby, qbz, P.max_d2, sta, da, pa, stb, db, pb);
-    if (sta != 1) pa = ax == ax ? general_nn(P.grid, qax, qay, qaz, P.max_d2) : -1;
-    if (stb != 1) pb = bx == bx ? general_nn(P.grid, qbx, qby, qbz, P.max_d2) : -1;
-    P.prev[ia] = pa;
-    P.prev[ib] = pb;
-}
-
 // DYNAMIC: warps fetch rows of 32 consecutive scan slots from a device-wide counter (P.grab_rows
 // rows per fetch) -- the cost of a row varies with the local geometry, and a static partition left
 // the slowest SM 30 % behind the average.  The parked result of a slot does not depend on who
 // computed it and the accumulate pass keeps its fixed order, so results stay deterministic.  Only
 // possible when the accumulate pass is a separate kernel (it reads slots parked by other blocks).
-// (A block-level queue that collected the list misses and searched them at the end of the block
-// was measured and removed: with dynamic rows it only serialises the stragglers into a tail.)
+// (Measured and removed: a block-level queue that collected the list misses and searched them at
+// the end of the block -- with dynamic rows it only serialises the stragglers into a tail; and two
+// list streams per lane -- no gain, the L1 tag stage is already 80 % busy, profiles/r1_notes.md.)
 template <int METHOD, bool DYNAMIC>
 __device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32& pose) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
@@ -254,17 +238,13 @@ __device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32
     const bool lists = kVoxel ? (P.use_lists != 0) : (P.use_shell != 0);
     if (DYNAMIC) {
         const int rows_total = (int)(P.n_pad >> 5);
-        const bool pairs = !kVoxel && lists && P.pair_rows;
         for (;;) {
             int r0 = 0;
             if (lane == 0) r0 = atomicAdd(&P.st->next_row, P.grab_rows);
             r0 = __shfl_sync(0xffffffffu, r0, 0);
             if (r0 >= rows_total) break;
             const int r1 = r0 + P.grab_rows < rows_total ? r0 + P.grab_rows : rows_total;
-            int r = r0;
-            if (pairs)
-                for (; r + 1 < r1; r += 2) correspond_slot_pair(P, pose, ((long long)r << 5) + lane, ((long long)(r + 1) << 5) + lane);
-            for (; r < r1; ++r) correspond_slot<METHOD>(P, pose, ((long long)r << 5) + lane, lists);
+            for (int r = r0; r < r1; ++r) correspond_slot<METHOD>(P, pose, ((long long)r << 5) + lane, lists);
         }
     } else {
         const long long stride = (long long)gridDim.x * kLinThreads;
@@ -409,8 +389,9 @@ __global__ void morton_key_kernel(const float* __restrict__ xyz, long long n, co
 // one or two cells and stream the SAME list, instead of 4-8 cells with a Morton order in the
 // scan's own frame.  A rigid motion moves the points of one cell together, so the order stays
 // coherent over the Gauss-Newton iterations.
+template <typename KEY>
 __global__ void cell_key_kernel(const float* __restrict__ xyz, long long n, GridView G, Pose32 pose,
-                                unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                KEY* __restrict__ keys, uint32_t* __restrict__ vals) {
     long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     float qx, qy, qz;
@@ -424,7 +405,7 @@ __global__ void cell_key_kernel(const float* __restrict__ xyz, long long n, Grid
     const int cy = cell_of(fminf(fmaxf(gy, -big), big), G.cny);
     const int cz = cell_of(fminf(fmaxf(gz, -big), big), G.cnz);
     const unsigned long long brick = ((unsigned long long)(cz >> 2) * G.bny + (cy >> 2)) * G.bnx + (cx >> 2);
-    keys[i] = brick * 64ull + (unsigned long long)brick_bit(cx, cy, cz);
+    keys[i] = (KEY)(brick * 64ull + (unsigned long long)brick_bit(cx, cy, cz));
     vals[i] = (uint32_t)i;
 }
 
@@ -585,13 +566,11 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
     P.shell = ctx->tgt_shell;
     P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
-    P.pair_rows = ctx->pair_rows;
     // rows per fetch: about 16 fetches per resident warp (one device-wide counter serves them all;
     // a fetch per row would make it the bottleneck of a 10M-point scan), at least 1
     {
-        const long long rows = ctx->n_scan_pad / 32, warps = (long long)ctx->sm_count * ctx->min_blocks * (kLinThreads / 32);
+        const long long rows = ctx->n_scan_pad / 32, warps = (long long)ctx->sm_count * 4 * (kLinThreads / 32);
         long long per = ctx->grab_rows > 0 ? ctx->grab_rows : rows / (warps * 16);
-        if (ctx->pair_rows && ctx->grab_rows <= 0) per = per < 2 ? 2 : (per + 1) / 2 * 2;   // whole pairs
         P.grab_rows = (int)(per < 1 ? 1 : (per > 64 ? 64 : per));
     }
     P.vrec = method == PCR_NDT ? ctx->vox_rec_ndt.as<float4>() : ctx->vox_rec_plane.as<float4>();
@@ -611,7 +590,10 @@ static int blocks_for_kernel(pcr_ctx* ctx, K kernel, int& cached, long long n_pa
 template <int METHOD>
 static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     // ctx->min_blocks = resident blocks per SM requested for the correspondence pass (2..6)
-    const int mb = ctx->min_blocks < 3 ? 3 : (ctx->min_blocks > 6 ? 6 : ctx->min_blocks);
+    // resident blocks per SM of the correspondence kernel: measured best 5 (48 registers) for the
+    // shell-list stream, 4 for the voxel candidate lists; PCR_MIN_BLOCKS overrides
+    int mb = ctx->min_blocks > 0 ? ctx->min_blocks : ((METHOD == PCR_METHOD_ICP || METHOD == PCR_METHOD_PLANE) ? 5 : 4);
+    mb = mb < 3 ? 3 : (mb > 6 ? 6 : mb);
     int* cache = ctx->lin_blocks_per_sm[METHOD];
     if (ctx->split_passes) {
         int blocks;
@@ -711,17 +693,27 @@ static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, co
             PCR_CUDA(ctx->tmp_a.ensure((size_t)n * 8));
             PCR_CUDA(ctx->tmp_b.ensure((size_t)n * 8));
             PCR_CUDA(ctx->tmp_d.ensure((size_t)n * 4 * 2));
-            unsigned long long* k_in = ctx->tmp_a.as<unsigned long long>();
-            unsigned long long* k_out = ctx->tmp_b.as<unsigned long long>();
             uint32_t* v_in = ctx->tmp_d.as<uint32_t>(); uint32_t* v_out = v_in + n;
-            cell_key_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, g->view, pose, k_in, v_in);
-            PCR_LAUNCH_CHECK();
             const unsigned long long nkeys = (unsigned long long)g->view.bnx * g->view.bny * g->view.bnz * 64ull;
             const int end_bit = bits_for_u64(nkeys);
             size_t tmp = 0;
-            PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
-            PCR_CUDA(ctx->cub_tmp.ensure(tmp));
-            PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
+            if (end_bit <= 32) {                                  // the usual case: 32-bit keys sort faster
+                uint32_t* k_in = ctx->tmp_a.as<uint32_t>();
+                uint32_t* k_out = ctx->tmp_b.as<uint32_t>();
+                cell_key_kernel<uint32_t><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, g->view, pose, k_in, v_in);
+                PCR_LAUNCH_CHECK();
+                PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
+                PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+                PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
+            } else {
+                unsigned long long* k_in = ctx->tmp_a.as<unsigned long long>();
+                unsigned long long* k_out = ctx->tmp_b.as<unsigned long long>();
+                cell_key_kernel<unsigned long long><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, n, g->view, pose, k_in, v_in);
+                PCR_LAUNCH_CHECK();
+                PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
+                PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+                PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, (long long)n, 0, end_bit, ctx->stream));
+            }
             ctx->launches += 4;
             order = v_out;
         } else {

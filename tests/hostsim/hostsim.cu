@@ -233,12 +233,19 @@ void hs_shell_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* 
         int pos;
         bool ok;
         if (pair) {
-            // the kernel's two-at-a-time stream: query i together with query m - 1 - i
-            const int64_t o = m - 1 - i;
-            int sta, stb, pb; float db;
-            shell_scan_pair(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], q[3 * o], q[3 * o + 1], q[3 * o + 2], md * md, sta, d2, pos, stb, db, pb);
-            ok = sta != 0;
-            if (sta == 2) { Best1 b; b.d2 = d2; b.pos = pos; grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], b); d2 = b.d2; pos = b.pos; }
+            // the cursor API used step by step, as a kernel would interleave it with other work
+            ShellCursor c;
+            ok = shell_open(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, c);
+            int st = 0;
+            if (ok) {
+                while (c.active) {
+                    const float4* g4 = g->shell.pts + c.k;
+                    shell_eval_group(g4[0], g4[1], g4[2], q[3 * i], q[3 * i + 1], q[3 * i + 2], c.k, c.best, c.best_k);
+                    shell_advance(c, g->shell.margin2[(c.k >> 2) + 1]);
+                }
+                st = shell_close(g->shell, c, d2, pos);
+            }
+            if (st == 2) { Best1 b; b.d2 = d2; b.pos = pos; grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], b); d2 = b.d2; pos = b.pos; }
         } else {
             ok = shell_nn(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
         }

@@ -153,7 +153,7 @@ def test_shell_lists_match_general_search(hs, dmax_frac):
             q = np.ascontiguousarray(q)
             i0 = np.empty(len(q), np.int64); d0 = np.empty(len(q), np.float32)
             hs.hs_nn(g, ptr(q), len(q), float(md), ptr(i0), ptr(d0))
-            for pair in (0, 1):                               # one query at a time / the kernel's two-at-a-time stream
+            for pair in (0, 1):                               # shell_nn / the cursor API step by step
                 i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32); used = np.zeros(len(q), np.uint8)
                 hs.hs_shell_nn(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1), ptr(used), pair)
                 assert np.array_equal(d0, d1)
