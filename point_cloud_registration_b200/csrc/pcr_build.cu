@@ -363,6 +363,15 @@ __global__ void scatter_normals_kernel(const float* __restrict__ nrm_orig, const
     nrm_sorted[i] = make_float4(nrm_orig[3 * j], nrm_orig[3 * j + 1], nrm_orig[3 * j + 2], 0.f);
 }
 
+// PlaneICP record: (point, normal) of one target point side by side -- ONE 32-byte sector per
+// gathered correspondence in the accumulate pass instead of two
+__global__ void interleave_pn_kernel(const float4* __restrict__ pts, const float4* __restrict__ nrm, long long n, float4* __restrict__ pn) {
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    pn[2 * i] = pts[i];
+    pn[2 * i + 1] = nrm[i];
+}
+
 // ---------------------------------------------------------------------------------------
 // voxel statistics
 // ---------------------------------------------------------------------------------------
@@ -1138,7 +1147,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     cudaSetDevice(ctx->device);
     pcr_comm_destroy(ctx);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    ctx->tgt_xyz.release(); ctx->tgt_grid.release(); ctx->tgt_nrm_sorted.release(); ctx->tgt_nrm_orig.release();
+    ctx->tgt_xyz.release(); ctx->tgt_grid.release(); ctx->tgt_nrm_sorted.release(); ctx->tgt_nrm_orig.release(); ctx->tgt_pn.release();
     ctx->vox_mean.release(); ctx->vox_cov.release(); ctx->vox_norm.release(); ctx->vox_icov.release(); ctx->vox_count.release();
     ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
     ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release();
@@ -1198,6 +1207,9 @@ int pcr_estimate_normals(pcr_ctx* ctx, int k) {
     else if (k <= 32) normals_kernel<32><<<blk, thr, 0, ctx->stream>>>(ctx->tgt_grid.view, k, ns, no);
     else normals_kernel<64><<<blk, thr, 0, ctx->stream>>>(ctx->tgt_grid.view, k, ns, no);
     PCR_LAUNCH_CHECK();
+    PCR_CUDA(ctx->tgt_pn.ensure((size_t)n * 2 * sizeof(float4)));
+    interleave_pn_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->tgt_grid.view.pts, ns, n, ctx->tgt_pn.as<float4>());
+    PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->has_normals = true;
     return PCR_OK;
@@ -1215,6 +1227,10 @@ int pcr_set_normals(pcr_ctx* ctx, const float* normals) {
                              is_device_pointer(normals) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
     scatter_normals_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->tgt_nrm_orig.as<float>(), ctx->tgt_grid.view.pts, n,
                                                                         ctx->tgt_nrm_sorted.as<float4>());
+    PCR_LAUNCH_CHECK();
+    PCR_CUDA(ctx->tgt_pn.ensure((size_t)n * 2 * sizeof(float4)));
+    interleave_pn_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(ctx->tgt_grid.view.pts, ctx->tgt_nrm_sorted.as<float4>(), n,
+                                                                      ctx->tgt_pn.as<float4>());
     PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->has_normals = true;

@@ -76,6 +76,7 @@ struct pcr_ctx {
     pcr::DevBuf tgt_xyz;          // float[3n], caller order
     pcr::Grid tgt_grid;           // NN index over target points (payload = caller index)
     pcr::DevBuf tgt_nrm_sorted;   // float4[n], same order as tgt_grid.pts
+    pcr::DevBuf tgt_pn;           // float4[2n]: (point, normal) interleaved in that order -- the record PlaneICP gathers
     pcr::DevBuf tgt_nrm_orig;     // float[3n], caller order
     bool has_normals = false;
     pcr::DevBuf shell_bricks, shell_start, shell_pts, shell_margin2;   // per-cell shell lists over the target grid

@@ -31,7 +31,7 @@ struct LinParams {
     const float* sx; const float* sy; const float* sz;   // SoA scan, padded to a multiple of 32 with NaN
     long long n_pad;                                     // padded point count
     GridView grid;                                       // target points (ICP/PLANE) or voxel means (VPLANE/NDT)
-    const float4* nrm;                                   // PLANE: normals in grid order
+    const float4* pn;                                    // PLANE: (point, normal) records in grid order, 32 B each
     const float4* vrec;                                  // VPLANE: 2 float4 / voxel, NDT: 3 float4 / voxel
     CandLists lists;                                     // VPLANE/NDT: per-cell candidate lists (null = absent)
     int use_lists;
@@ -70,8 +70,8 @@ __device__ __forceinline__ void fetch_match(const LinParams& P, int pos, MatchRe
     if (METHOD == PCR_METHOD_ICP) {
         r.a = __ldg(P.grid.pts + pos);
     } else if (METHOD == PCR_METHOD_PLANE) {
-        r.a = __ldg(P.grid.pts + pos);
-        r.b = __ldg(P.nrm + pos);
+        r.a = __ldg(P.pn + 2 * (size_t)pos);
+        r.b = __ldg(P.pn + 2 * (size_t)pos + 1);
     } else if (METHOD == PCR_METHOD_VPLANE) {
         r.a = __ldg(P.vrec + 2 * (size_t)pos);
         r.b = __ldg(P.vrec + 2 * (size_t)pos + 1);
@@ -560,7 +560,7 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.sx = ctx->scan_x.as<float>(); P.sy = ctx->scan_y.as<float>(); P.sz = ctx->scan_z.as<float>();
     P.n_pad = ctx->n_scan_pad;
     P.grid = (method == PCR_ICP || method == PCR_PLANE) ? ctx->tgt_grid.view : ctx->vox_grid.view;
-    P.nrm = ctx->tgt_nrm_sorted.as<float4>();
+    P.pn = ctx->tgt_pn.as<float4>();
     P.prev = ctx->scan_prev.as<int>();
     P.lists = ctx->vox_lists;
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
