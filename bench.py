@@ -17,8 +17,8 @@ Workloads (BASELINE.json `configs`):
 
 Timed regions (b200 arm)
   value     device-resident: scan + target structures in HBM, K iterations of the on-device loop
-            (fused linearise kernel whose last block also solves and updates T); every
-            iteration timed with its own CUDA-event pair on the library's stream, L2 flushed
+            (correspond kernel + accumulate kernel, whose last block also solves and updates T);
+            every iteration timed with its own CUDA-event pair on the library's stream, L2 flushed
             (512 MiB memset) between iterations, outside the event pairs; max over ranks.
   warm_l2   the same loop enqueued back to back without flushing (what align() really does).
   e2e       through the drop-in Python class with HOST buffers: every step calls
@@ -410,8 +410,9 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, light=False)
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes, "bytes_per_scan_point": wl["bytes_per_point"],
-                         "kernel": f"linearize_lane_kernel<{wl['cls']}> (fused transform + exact correspondence (per-cell list stream, "
-                                   f"straggler queue) + residual/Jacobian + reduction + GN step)"},
+                         "kernel": f"correspond_kernel<{wl['cls']}> (SE(3) transform + exact correspondence by per-cell list stream) + "
+                                   f"accumulate_kernel<{wl['cls']}> (gather + residual/Jacobian + reduction + GN step); achieved = "
+                                   "algorithmic bytes / CUDA-event time of the pair; traffic = ncu DRAM bytes of the pair per iteration"},
             "cpu_baseline": cpu_baseline,
             "e2e": e2e,
             "gpu_launches": int(launches),
