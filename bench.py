@@ -40,6 +40,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+RESULT_OUT = sys.stdout
 METRIC = "ICP iterations/sec"
 UNIT = "iterations/s"
 
@@ -194,7 +195,7 @@ def run_reference(args, wl_name, wl, world, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=RESULT_OUT, flush=True)
 
 
 def workload_config(wl_name, wl, world, n_total):
@@ -435,6 +436,13 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, light=False)
 
 
 def main():
+    # The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version
+    # banner from C): keep a private handle on the real stdout for the final line and point fd 1 at
+    # stderr for everything else.
+    global RESULT_OUT
+    sys.stdout.flush()
+    RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
@@ -476,7 +484,7 @@ def main():
                 others.append({"workload": name, "error": repr(e)})
         line["other_workloads"] = others
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=RESULT_OUT, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -66,6 +66,10 @@ int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n);
 /* Build the exact nearest-neighbour index over the target points.  Replaces
  * `KDTree(target)` (kdtree.py:18-25 -> pykdtree; icp.py:20, plane_icp.py:22). */
 int pcr_build_nn_index(pcr_ctx* ctx);
+/* Build the per-cell shell lists the ICP / PlaneICP correspondence pass streams (needs the NN
+ * index; part of ICP.set_target / PlaneICP.set_target, not of KDTree()).  Built implicitly by the
+ * first linearisation if it was not called. */
+int pcr_build_correspondence_lists(pcr_ctx* ctx);
 
 /* k-NN normal estimation on the device; k includes the point itself; float32 moment
  * formula of the reference replayed (quirk Q5).  Replaces estimate_norm_with_tree

@@ -31,6 +31,7 @@ SYMBOLS = {
     "pcr_last_error": (C.c_char_p, [_vp]),
     "pcr_set_target_points": (_i, [_vp, _vp, _i64]),
     "pcr_build_nn_index": (_i, [_vp]),
+    "pcr_build_correspondence_lists": (_i, [_vp]),
     "pcr_estimate_normals": (_i, [_vp, _i]),
     "pcr_set_normals": (_i, [_vp, _vp]),
     "pcr_get_normals": (_i, [_vp, _vp]),
@@ -190,6 +191,9 @@ class Context:
 
     def build_nn_index(self):
         self._check(self._lib.pcr_build_nn_index(self._h))
+
+    def build_correspondence_lists(self):
+        self._check(self._lib.pcr_build_correspondence_lists(self._h))
 
     def estimate_normals(self, k):
         self._check(self._lib.pcr_estimate_normals(self._h, int(k)))

@@ -1172,6 +1172,7 @@ int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n) {
     ctx->tgt_grid.release();
     ctx->tgt_shell = ShellLists{};              // lists refer to the released grid
     ctx->n_shell_band = ctx->n_shell_entries = 0;
+    ctx->shell_tried = false;
     ctx->has_normals = false;
     PCR_CUDA(ctx->tgt_xyz.ensure((size_t)n * 12));
     PCR_CUDA(cudaMemcpyAsync(ctx->tgt_xyz.p, xyz, (size_t)n * 12,
@@ -1186,8 +1187,18 @@ int pcr_build_nn_index(pcr_ctx* ctx) {
     if (ctx->n_tgt <= 0) return fail(ctx, PCR_ERR_STATE, "pcr_build_nn_index: target points not set");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->tgt_grid_epoch++;
-    int rc = build_point_grid(ctx, ctx->tgt_xyz.as<float>(), ctx->n_tgt, ctx->tgt_grid, nullptr);
-    if (rc) return rc;
+    ctx->tgt_shell = ShellLists{};              // lists of the previous grid are void; rebuilt on demand
+    ctx->n_shell_band = ctx->n_shell_entries = 0;
+    ctx->shell_dmax_used = 0.0;
+    ctx->shell_tried = false;
+    return build_point_grid(ctx, ctx->tgt_xyz.as<float>(), ctx->n_tgt, ctx->tgt_grid, nullptr);
+}
+
+int pcr_build_correspondence_lists(pcr_ctx* ctx) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "pcr_build_correspondence_lists: NN index not built");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    ctx->shell_tried = true;
     return build_shell_lists(ctx);
 }
 

@@ -82,6 +82,7 @@ struct pcr_ctx {
     pcr::DevBuf shell_bricks, shell_start, shell_pts, shell_margin2;   // per-cell shell lists over the target grid
     pcr::ShellLists tgt_shell{};  // null pointers = not built
     long long n_shell_band = 0, n_shell_entries = 0;
+    bool shell_tried = false;     // pcr_build_correspondence_lists ran for the current grid
     int use_shell_lists = 1;
     double shell_dmax_frac = 2.0; // requested list margin in cell edges (<= 2); reduced until the lists fit shell_max_gib
     double shell_max_gib = 24.0;  // memory cap of the lists

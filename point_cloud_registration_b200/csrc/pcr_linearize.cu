@@ -615,7 +615,15 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     return PCR_OK;
 }
 
-static int launch_linearize(pcr_ctx* ctx, int method, const LinParams& P) {
+static int launch_linearize(pcr_ctx* ctx, int method, LinParams& P) {
+    // target-point methods stream shell lists: build them now if the caller did not (C-ABI users
+    // that skipped pcr_build_correspondence_lists still get the fast path, one call late)
+    if ((method == PCR_ICP || method == PCR_PLANE) && !ctx->shell_tried) {
+        int rc = pcr_build_correspondence_lists(ctx);
+        if (rc) return rc;
+        P.shell = ctx->tgt_shell;
+        P.use_shell = ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
+    }
     // warm-start positions refer to one particular index: forget them when it changed
     const int which = (method == PCR_ICP || method == PCR_PLANE) ? 0 : 1;
     const long long epoch = which == 0 ? ctx->tgt_grid_epoch : ctx->vox_grid_epoch;

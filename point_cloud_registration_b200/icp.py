@@ -21,4 +21,5 @@ class ICP(Registration):
         self.kdtree = KDTree(target, device=self._device)
         self.target = self.kdtree.data
         self._ctx = self.kdtree._ctx
+        self._ctx.build_correspondence_lists()           # shell lists streamed by the correspondence pass
         self._is_target_set = True

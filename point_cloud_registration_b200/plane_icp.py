@@ -28,6 +28,7 @@ class PlaneICP(Registration):
         else:
             self.kdtree = KDTree(self.target, device=self._device)
         self._ctx = self.kdtree._ctx
+        self._ctx.build_correspondence_lists()           # shell lists streamed by the correspondence pass
         if kdree is None or norm is None:
             self._ctx.estimate_normals(self.k)
             self._normal = None
