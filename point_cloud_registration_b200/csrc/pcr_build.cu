@@ -886,6 +886,10 @@ __global__ void shell_build_kernel(GridView G, const BrickRec* __restrict__ band
     }
 }
 
+struct U32ToU64 {
+    __host__ __device__ unsigned long long operator()(uint32_t v) const { return (unsigned long long)v; }
+};
+
 static int build_shell_lists(pcr_ctx* ctx) {
     Grid& g = ctx->tgt_grid;
     ctx->tgt_shell = ShellLists{};
@@ -931,9 +935,10 @@ static int build_shell_lists(pcr_ctx* ctx) {
         size_t tmp = 0;
         PCR_CUDA(ctx->tmp_e.ensure(64));
         unsigned long long* d_total = ctx->tmp_e.as<unsigned long long>();
-        PCR_CUDA(cub::DeviceReduce::Sum(nullptr, tmp, counts, d_total, (long long)n_band, ctx->stream));
+        cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> counts64(counts, U32ToU64());   // 64-bit accumulation
+        PCR_CUDA(cub::DeviceReduce::Sum(nullptr, tmp, counts64, d_total, (long long)n_band, ctx->stream));
         PCR_CUDA(ctx->cub_tmp.ensure(tmp));
-        PCR_CUDA(cub::DeviceReduce::Sum(ctx->cub_tmp.p, tmp, counts, d_total, (long long)n_band, ctx->stream));
+        PCR_CUDA(cub::DeviceReduce::Sum(ctx->cub_tmp.p, tmp, counts64, d_total, (long long)n_band, ctx->stream));
         ctx->launches += 1;
         unsigned long long total = 0;
         PCR_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
