@@ -1138,6 +1138,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 24.0;
     if (const char* e = getenv("PCR_LIST_DILATE")) ctx->list_dilate = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 3;
     if (const char* e = getenv("PCR_LIST_RADIUS")) ctx->list_radius = atoi(e) >= 2 && atoi(e) <= 6 ? atoi(e) : 5;
+    if (const char* e = getenv("PCR_BALL_FIRST")) ctx->ball_first = atoi(e) != 0;
     if (const char* e = getenv("PCR_CELL_ORDER")) ctx->cell_order = atoi(e) != 0;
     if (const char* e = getenv("PCR_GRAB_ROWS")) ctx->grab_rows = atoi(e) >= 0 && atoi(e) <= 64 ? atoi(e) : 0;
     if (const char* e = getenv("PCR_SPLIT")) ctx->split_passes = atoi(e) != 0;

@@ -110,6 +110,7 @@ struct pcr_ctx {
     bool scan_sorted = false;     // spatially coherent order (Morton-sorted on upload, or promised by the caller)
     double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
     int min_blocks = 0;           // resident blocks per SM requested for the correspondence pass (3..6; 0: per-method default)
+    int ball_first = 1;           // list misses search the ball of max_dist in one pass (0: ring growth, A/B)
     int cell_order = 1;           // scan upload: order by correspondence-grid cell (0: Morton order in the scan's frame)
     int grab_rows = 0;            // rows of 32 scan slots a warp fetches at a time (0: chosen from the scan size)
     int split_passes = 1;         // 1: correspond + accumulate kernels, 0: one fused kernel (A/B)

@@ -198,8 +198,12 @@ PCR_HD void grid_search_continue(const GridView& G, float qx, float qy, float qz
 }
 
 // Generic exact search.  `best` carries the initial radius (max_dist^2) and receives results.
+// ball_first: the caller knows that nothing lies near the query (its cell's list was exhausted, or
+// the cell is not even close to an occupied one): skip the ring-by-ring growth, which would re-walk
+// the neighbourhood once per ring, and visit the cell box of the ball (query, radius) in ONE pruned
+// pass -- provided that box is small (a bounded max_dist); otherwise grow rings as usual.
 template <class Best>
-PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& best) {
+PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& best, bool ball_first = false) {
     if (G.n_pts == 0) return;
     const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
     if (!(gx == gx) || !(gy == gy) || !(gz == gz)) return;            // NaN query: no match
@@ -216,16 +220,20 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
     const float cgx = fminf(fmaxf(gx, -big), big), cgy = fminf(fmaxf(gy, -big), big), cgz = fminf(fmaxf(gz, -big), big);
     Block3 cur;
     Block3 none; none.x0 = none.y0 = none.z0 = 0; none.x1 = none.y1 = none.z1 = -1;
-    if (best.have()) {
-        // warm start: the caller already holds a candidate (an upper bound).  Every closer point
-        // lies in a cell meeting the ball (query, bound): visit exactly that box and stop.
+    if (best.have() || ball_first) {
+        // warm start: the caller already holds a candidate (an upper bound), or asks for the ball of
+        // the search radius.  Every closer point lies in a cell meeting the ball (query, bound):
+        // visit exactly that box and stop.
         const float r = sqrtf(best.radius2()) * G.inv_h * 1.000001f + G.slack;
         cur.x0 = cell_of(fminf(fmaxf(gx - r, -big), big), G.cnx); cur.x1 = cell_of(fminf(fmaxf(gx + r, -big), big), G.cnx);
         cur.y0 = cell_of(fminf(fmaxf(gy - r, -big), big), G.cny); cur.y1 = cell_of(fminf(fmaxf(gy + r, -big), big), G.cny);
         cur.z0 = cell_of(fminf(fmaxf(gz - r, -big), big), G.cnz); cur.z1 = cell_of(fminf(fmaxf(gz + r, -big), big), G.cnz);
-        if (is_small_box(cur)) visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
-        else visit_block(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
-        return;
+        const bool small_ball = (cur.x1 - cur.x0) < 24 && (cur.y1 - cur.y0) < 24 && (cur.z1 - cur.z0) < 24;   // <= 7 bricks per axis
+        if (best.have() || small_ball) {
+            if (is_small_box(cur)) visit_small_box(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+            else visit_block(G, qx, qy, qz, gx, gy, gz, cur, none, false, best);
+            return;
+        }
     }
     cur.x0 = cur.x1 = cell_of(cgx, G.cnx);
     cur.y0 = cur.y1 = cell_of(cgy, G.cny);
@@ -235,9 +243,9 @@ PCR_HD void grid_search(const GridView& G, float qx, float qy, float qz, Best& b
 }
 
 // 1-NN convenience wrapper: returns position in G.pts (or -1) and the squared distance.
-PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2, float& out_d2) {
+PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2, float& out_d2, bool ball_first = false) {
     Best1 b; b.d2 = max_d2; b.pos = -1;
-    grid_search(G, qx, qy, qz, b);
+    grid_search(G, qx, qy, qz, b, ball_first);
     out_d2 = b.d2;
     return b.pos;
 }

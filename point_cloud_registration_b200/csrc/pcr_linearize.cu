@@ -37,6 +37,7 @@ struct LinParams {
     int use_lists;
     ShellLists shell;                                    // ICP/PLANE: per-cell shell lists (null = absent)
     int use_shell;
+    int ball_first;                                      // list misses: one pass over the ball of max_dist instead of ring growth
     int grab_rows;                                       // rows of 32 scan slots a warp fetches at a time (correspondence pass)
     int* prev;                                           // per scan slot: position matched by the previous linearisation (-1 none)
     float max_d2;
@@ -192,10 +193,12 @@ __device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, P
 
 // The general brick-grid search as an out-of-line call: it only serves stragglers, and inlined it
 // would set the register budget (and so the occupancy) of the list-streaming loop around it.
-__device__ __noinline__ int general_nn(const GridView G, float qx, float qy, float qz, float max_d2) {   // by value: the kernel
+// far: the query's list found nothing near it -- one pruned pass over the ball of max_dist instead of
+// growing ring by ring (see grid_search).
+__device__ __noinline__ int general_nn(const GridView G, float qx, float qy, float qz, float max_d2, bool far) {   // by value: the kernel
     // parameter block stays in the constant bank instead of being copied to local memory for its address
     float d2;
-    return grid_nn(G, qx, qy, qz, max_d2, d2);
+    return grid_nn(G, qx, qy, qz, max_d2, d2, far);
 }
 
 // ---- pass 1: correspondences ---------------------------------------------------------------------
@@ -218,7 +221,7 @@ __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32
             if (kVoxel) settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
             else settled = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) == 1;
         }
-        if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2);
+        if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2, lists && P.ball_first);
     }
     P.prev[i] = pos;
 }
@@ -566,6 +569,7 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
     P.shell = ctx->tgt_shell;
     P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
+    P.ball_first = ctx->ball_first;
     // rows per fetch: about 16 fetches per resident warp (one device-wide counter serves them all;
     // a fetch per row would make it the bottleneck of a 10M-point scan), at least 1
     {

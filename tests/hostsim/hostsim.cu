@@ -101,6 +101,21 @@ void hs_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, f
     }
 }
 
+// grid_nn with ball_first (the kernels' path for list misses)
+void hs_nn_ball_first(void* gp, const float* q, int64_t m, double max_dist, int64_t* idx, float* dist) {
+    const GridView& G = ((HostGrid*)gp)->v;
+    const float md = (float)max_dist;
+    for (int64_t i = 0; i < m; ++i) {
+        float d2;
+        int pos = grid_nn(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, true);
+        if (pos >= 0) {
+            uint32_t j;
+            memcpy(&j, &G.pts[pos].w, 4);
+            idx[i] = j; dist[i] = sqrtf(d2);
+        } else { idx[i] = -1; dist[i] = INFINITY; }
+    }
+}
+
 void hs_knn(void* gp, const float* q, int64_t m, int k, int64_t* idx, float* dist) {
     const GridView& G = ((HostGrid*)gp)->v;
     for (int64_t i = 0; i < m; ++i) {

@@ -34,6 +34,7 @@ def hs():
     lib.hs_shell_build.restype = C.c_int64
     lib.hs_shell_build.argtypes = [C.c_void_p, C.c_double]
     lib.hs_shell_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.hs_nn_ball_first.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]
     lib.hs_knn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]
     lib.hs_linearize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.hs_gn_step.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -160,6 +161,26 @@ def test_shell_lists_match_general_search(hs, dmax_frac):
                 assert np.array_equal(i0 < 0, i1 < 0) and (i0 == i1).mean() > 0.999
                 if expect_lists:
                     assert used.mean() > 0.5
+        hs.hs_grid_free(g)
+
+
+def test_ball_first_search_matches_ring_growth(hs):
+    """grid_search(ball_first=True) -- one pruned pass over the ball of max_dist, the kernels' path
+    for list misses -- returns what the ring-by-ring search returns, for bounded and huge max_dist."""
+    rng = np.random.default_rng(9)
+    pts = ds.make_urban_slab(20000, seed=7)
+    near = ds.perturb_scan(pts, seed=3)[:2000]
+    far = near[:700] + np.array([0, 0, 1.7], dtype=np.float32)
+    box = (rng.random((800, 3)) * (pts.max(0) - pts.min(0) + 6) + pts.min(0) - 3).astype(np.float32)
+    for h in (0.1, 0.4, 1.5):
+        g = hs.hs_grid_build(ptr(pts), len(pts), float(h))
+        for q, md in ((near, 2.0), (far, 2.0), (far, 1.0), (box, 2.0), (box, 0.3), (far, 1e9)):
+            q = np.ascontiguousarray(q)
+            i0 = np.empty(len(q), np.int64); d0 = np.empty(len(q), np.float32)
+            hs.hs_nn(g, ptr(q), len(q), float(md), ptr(i0), ptr(d0))
+            i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32)
+            hs.hs_nn_ball_first(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1))
+            assert np.array_equal(d0, d1) and np.array_equal(i0 < 0, i1 < 0) and (i0 == i1).mean() > 0.999
         hs.hs_grid_free(g)
 
 
