@@ -194,16 +194,11 @@ __device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, P
 // The general brick-grid search as an out-of-line call: it only serves stragglers, and inlined it
 // would set the register budget (and so the occupancy) of the list-streaming loop around it.
 // far: the query's list found nothing near it -- one pruned pass over the ball of max_dist instead of
-// growing ring by ring (see grid_search).  warm_pos >= 0: the list did find a candidate (squared
-// distance warm_d2) but could not prove it nearest: only the ball of that candidate is searched.
-__device__ __noinline__ int general_nn(const GridView G, float qx, float qy, float qz, float max_d2, bool far, float warm_d2, int warm_pos) {
-    // (GridView by value: the kernel parameter block stays in the constant bank instead of being
-    // copied to local memory for its address)
-    Best1 b;
-    b.d2 = warm_pos >= 0 ? warm_d2 : max_d2;
-    b.pos = warm_pos;
-    grid_search(G, qx, qy, qz, b, far);
-    return b.pos;
+// growing ring by ring (see grid_search).
+__device__ __noinline__ int general_nn(const GridView G, float qx, float qy, float qz, float max_d2, bool far) {   // by value: the kernel
+    // parameter block stays in the constant bank instead of being copied to local memory for its address
+    float d2;
+    return grid_nn(G, qx, qy, qz, max_d2, d2, far);
 }
 
 // ---- pass 1: correspondences ---------------------------------------------------------------------
@@ -219,20 +214,14 @@ __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32
     const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
     int pos = -1;
     if (px == px) {                                              // NaN = padding: no match
-        float qx, qy, qz, d2 = P.max_d2;
+        float qx, qy, qz, d2;
         transform32(pose, px, py, pz, qx, qy, qz);
         bool settled = false;
-        int warm = -1;                                           // candidate the list found but could not prove nearest
         if (lists) {
-            if (kVoxel) {
-                settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
-            } else {
-                const int st = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos);
-                settled = st == 1;
-                if (st == 2) warm = pos;
-            }
+            if (kVoxel) settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
+            else settled = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) == 1;
         }
-        if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2, lists && P.ball_first, d2, warm);
+        if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2, lists && P.ball_first);
     }
     P.prev[i] = pos;
 }
