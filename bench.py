@@ -422,7 +422,6 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, light=False)
             "transform_err_vs_ref": transform_err,
             "align_iterations": m,
             "step_ms_by_iteration": [float(step_ms[j::m].mean()) for j in range(m)] if K >= m else None,
-            "tile_lanes": os.environ.get("PCR_TILE_LANES", "default"),
             "set_target_s": set_target_s, "scan_upload_sort_ms": set_scan_s * 1e3,
             "wall_ms_per_step_incl_flush": wall_s * 1e3 / K,
             "points_per_sec": value * n_total,

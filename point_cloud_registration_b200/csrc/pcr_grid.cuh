@@ -348,8 +348,8 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
     return shell_close(S, c, out_d2, out_pos);
 }
 
-// 1-NN through the shell lists with the general search as continuation (host replay, and the
-// kernels' inline path when the straggler queue is full or disabled).  false: the cell has no list.
+// 1-NN through the shell lists with the general search as continuation, warm-started from the
+// list's bound (host replay of the list path).  false: the cell has no list.
 PCR_HD bool shell_nn(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
     const int st = shell_scan(G, S, qx, qy, qz, max_d2, out_d2, out_pos);
     if (st == 0) return false;

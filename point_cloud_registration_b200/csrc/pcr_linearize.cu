@@ -202,12 +202,10 @@ __device__ __noinline__ int general_nn(const GridView G, float qx, float qy, flo
 }
 
 // ---- pass 1: correspondences ---------------------------------------------------------------------
-// 1a: every query streams the list of its cell -- lanes of one cell read the same addresses for
-// nearly the same number of steps.  The few queries a list cannot settle (no list for the cell,
-// or the best still beyond the listed margin) are NOT searched here, where they would stall the
-// other 31 lanes of their warp: their scan slots go to a block queue.  1b: the block works the
-// queue off with every lane busy (general brick-grid search).
-// one scan slot: list stream; the general search for what no list can settle
+// Every query streams the list of its cell -- lanes of one cell read the same addresses for nearly
+// the same number of steps.  The few queries a list cannot settle (no list for the cell, or the
+// best still beyond the listed margin) run the general brick-grid search in place.
+// one scan slot:
 template <int METHOD>
 __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32& pose, long long i, bool lists) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
