@@ -962,6 +962,7 @@ static int build_shell_lists(pcr_ctx* ctx) {
         ctx->tgt_shell.margin2 = ctx->shell_margin2.as<float>();
         const float cov = fmaxf(dmax - G.slack * G.h, 0.0f);
         ctx->tgt_shell.covered2 = cov * cov;
+        ctx->tgt_shell.block_r = (double)dmax >= 1.7320508 * (double)G.h * 1.0001 ? 1 : 0;
         ctx->n_shell_band = n_band;
         ctx->n_shell_entries = n_entries;
         ctx->shell_dmax_used = frac;

@@ -183,6 +183,8 @@ struct ShellLists {
     const float4* pts;           // entries (+ 4 sentinels)
     const float* margin2;        // [entries / 4]
     float covered2;              // (dmax - slack)^2: a best within it after the whole list is final
+    int block_r;                 // the lists hold EVERY point of the (2 block_r + 1)^3 cell block around their cell
+                                 // (1 when dmax >= sqrt(3) cell edges, else 0: only the cell itself)
 };
 
 PCR_HD int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -32,6 +32,21 @@ struct Best1 {
     }
 };
 
+// Policy for the continuation of a search whose first part was answered by a list: `d2` / `pos`
+// hold the list's best, which prunes like a found candidate, but the search keeps growing ring by
+// ring (have() is false) until the walk itself finds something closer -- the ball of the list's
+// candidate is usually much larger than the one the true neighbour needs.
+struct BestSeeded {
+    float d2;
+    int pos;
+    bool improved;
+    PCR_HD bool have() const { return improved; }
+    PCR_HD float radius2() const { return d2; }
+    PCR_HD void offer(float cand_d2, int cand_pos) {
+        if (cand_d2 < d2) { d2 = cand_d2; pos = cand_pos; improved = true; }
+    }
+};
+
 // Policy for k-NN: ascending sorted list in caller-provided storage.
 template <int KCAP>
 struct BestK {
@@ -348,16 +363,29 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
     return shell_close(S, c, out_d2, out_pos);
 }
 
-// 1-NN through the shell lists with the general search as continuation, warm-started from the
-// list's bound (host replay of the list path).  false: the cell has no list.
+// Continuation of a list scan that ended with status 2: the list evaluated every point of the
+// (2 block_r + 1)^3 cell block around the query's cell, so the brick-grid search resumes OUTSIDE
+// that block, ring by ring, pruned by the list's best (in/out: out_d2, out_pos).
+PCR_HD void shell_continue(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float& out_d2, int& out_pos) {
+    const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
+    const int cx = (int)gx, cy = (int)gy, cz = (int)gz;       // inside the grid: shell_open accepted the query
+    const int r = S.block_r;
+    Block3 cur;
+    cur.x0 = cx - r > 0 ? cx - r : 0; cur.x1 = cx + r < G.cnx - 1 ? cx + r : G.cnx - 1;
+    cur.y0 = cy - r > 0 ? cy - r : 0; cur.y1 = cy + r < G.cny - 1 ? cy + r : G.cny - 1;
+    cur.z0 = cz - r > 0 ? cz - r : 0; cur.z1 = cz + r < G.cnz - 1 ? cz + r : G.cnz - 1;
+    BestSeeded b;
+    b.d2 = out_d2; b.pos = out_pos; b.improved = false;
+    grid_search_continue(G, qx, qy, qz, gx, gy, gz, cur, b);
+    out_d2 = b.d2; out_pos = b.pos;
+}
+
+// 1-NN through the shell lists with the brick-grid search as continuation (what the kernel does
+// per scan slot; also the host replay).  false: the cell has no list.
 PCR_HD bool shell_nn(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, float& out_d2, int& out_pos) {
     const int st = shell_scan(G, S, qx, qy, qz, max_d2, out_d2, out_pos);
     if (st == 0) return false;
-    if (st == 2) {
-        Best1 b; b.d2 = out_d2; b.pos = out_pos;
-        grid_search(G, qx, qy, qz, b);                        // warm start from the list's bound
-        out_d2 = b.d2; out_pos = b.pos;
-    }
+    if (st == 2) shell_continue(G, S, qx, qy, qz, out_d2, out_pos);
     return true;
 }
 

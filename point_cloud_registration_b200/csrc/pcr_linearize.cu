@@ -201,6 +201,12 @@ __device__ __noinline__ int general_nn(const GridView G, float qx, float qy, flo
     return grid_nn(G, qx, qy, qz, max_d2, d2, far);
 }
 
+// Continuation of an exhausted shell list (out of line, like general_nn).
+__device__ __noinline__ int shell_continue_nn(const GridView G, const ShellLists S, float qx, float qy, float qz, float d2, int pos) {
+    shell_continue(G, S, qx, qy, qz, d2, pos);
+    return pos;
+}
+
 // ---- pass 1: correspondences ---------------------------------------------------------------------
 // Every query streams the list of its cell -- lanes of one cell read the same addresses for nearly
 // the same number of steps.  The few queries a list cannot settle (no list for the cell, or the
@@ -216,8 +222,15 @@ __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32
         transform32(pose, px, py, pz, qx, qy, qz);
         bool settled = false;
         if (lists) {
-            if (kVoxel) settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
-            else settled = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos) == 1;
+            if (kVoxel) {
+                settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
+            } else {
+                const int st = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos);
+                settled = st != 0;
+                // list exhausted before the best was proven nearest: the search resumes outside
+                // the block of cells the list covered, pruned by the list's best
+                if (st == 2) pos = shell_continue_nn(P.grid, P.shell, qx, qy, qz, d2, pos);
+            }
         }
         if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2, lists && P.ball_first);
     }

@@ -234,6 +234,7 @@ int64_t hs_shell_build(void* gp, double dmax_frac) {
     g->shell.margin2 = g->shell_margin2.data();
     const float cov = fmaxf(dmax - slack_w, 0.0f);
     g->shell.covered2 = cov * cov;
+    g->shell.block_r = (double)dmax >= 1.7320508 * (double)G.h * 1.0001 ? 1 : 0;
     return n_entries;
 }
 
@@ -260,7 +261,7 @@ void hs_shell_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* 
                 }
                 st = shell_close(g->shell, c, d2, pos);
             }
-            if (st == 2) { Best1 b; b.d2 = d2; b.pos = pos; grid_search(G, q[3 * i], q[3 * i + 1], q[3 * i + 2], b); d2 = b.d2; pos = b.pos; }
+            if (st == 2) shell_continue(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], d2, pos);
         } else {
             ok = shell_nn(G, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
         }
