@@ -164,6 +164,35 @@ def test_shell_lists_match_general_search(hs, dmax_frac):
         hs.hs_grid_free(g)
 
 
+def test_shell_lists_degenerate(hs):
+    """Shell lists on degenerate targets: a line, one point, duplicates, huge coordinates, a target
+    that sits in a single cell -- same answers as the brick-grid search."""
+    rng = np.random.default_rng(12)
+    line = np.zeros((300, 3), dtype=np.float32)
+    line[:, 0] = np.linspace(0, 10, 300)
+    one = np.array([[1.0, 2.0, 3.0]], dtype=np.float32)
+    dup = np.repeat(rng.random((50, 3)).astype(np.float32), 4, axis=0)
+    big = (rng.random((2000, 3)) * 800 - 400).astype(np.float32)
+    blob = (rng.random((500, 3)) * 0.01 + 5.0).astype(np.float32)
+    cases = ((line, 0.1, (rng.random((400, 3)) * np.array([12, 1, 1]) - np.array([1, 0.5, 0.5])).astype(np.float32)),
+             (one, 0.5, (rng.random((200, 3)) * 4).astype(np.float32)),
+             (dup, 0.1, np.concatenate([dup, dup + np.float32(0.03)])),
+             (big, 25.0, (rng.random((500, 3)) * 900 - 450).astype(np.float32)),
+             (blob, 1.0, (rng.random((300, 3)) * 3 + 3.5).astype(np.float32)))
+    for pts, h, q in cases:
+        q = np.ascontiguousarray(q)
+        for frac in (2.0, 1.0):
+            g = hs.hs_grid_build(ptr(pts), len(pts), float(h))
+            assert hs.hs_shell_build(g, frac) >= len(pts)
+            for md in (2.0, 1e9, 0.05):
+                i0 = np.empty(len(q), np.int64); d0 = np.empty(len(q), np.float32)
+                hs.hs_nn(g, ptr(q), len(q), float(md), ptr(i0), ptr(d0))
+                i1 = np.empty(len(q), np.int64); d1 = np.empty(len(q), np.float32); used = np.zeros(len(q), np.uint8)
+                hs.hs_shell_nn(g, ptr(q), len(q), float(md), ptr(i1), ptr(d1), ptr(used), 0)
+                assert np.array_equal(d0, d1) and np.array_equal(i0 < 0, i1 < 0)
+            hs.hs_grid_free(g)
+
+
 def test_ball_first_search_matches_ring_growth(hs):
     """grid_search(ball_first=True) -- one pruned pass over the ball of max_dist, the kernels' path
     for list misses -- returns what the ring-by-ring search returns, for bounded and huge max_dist."""
