@@ -275,6 +275,17 @@ void hs_shell_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* 
     }
 }
 
+// Development aid: status of the list scan per query (0 no list, 1 settled, 2 exhausted) and its distance.
+void hs_shell_status(void* gp, const float* q, int64_t m, double max_dist, int32_t* status, float* dist) {
+    HostGrid* g = (HostGrid*)gp;
+    const float md = (float)max_dist;
+    for (int64_t i = 0; i < m; ++i) {
+        float d2; int pos;
+        status[i] = shell_scan(g->v, g->shell, q[3 * i], q[3 * i + 1], q[3 * i + 2], md * md, d2, pos);
+        dist[i] = pos >= 0 ? sqrtf(d2) : INFINITY;
+    }
+}
+
 // Development aid: per warp row of 32 consecutive queries, groups of four evaluated by the
 // shell-list loop: out[0] = sum over rows of the max over lanes (lock-step cost), out[1] = sum
 // over all queries, out[2] = queries that fell back to the general search after the list,
