@@ -55,6 +55,9 @@ WORKLOADS = {
                desc="PlaneICP k=15, scan tile-sharded, 12.5M scan pts per GPU, target replicated"),
 }
 MAX_DIST, MAX_ITER, TOL = 2.0, 30, 1e-3
+if os.environ.get("PCR_BENCH_TEST_N"):          # test hook (tests/test_bench_contract.py): shrink every workload
+    for _w in WORKLOADS.values():
+        _w["n"] = int(os.environ["PCR_BENCH_TEST_N"])
 
 
 def log(*a):
