@@ -282,6 +282,40 @@ def test_terms_against_oracle(hs, method, Tname):
     assert abs(out[27] - e2) < 2e-5 * e2
 
 
+@pytest.mark.parametrize("method", [orc.ICP, orc.PLANE])
+def test_host_replay_of_one_linearisation(hs, method):
+    """The kernel pair replayed end to end on the host: transform -> shell-list correspondences
+    (device code compiled for the CPU) -> per-point terms -> record; against the oracle's
+    calc_H_g_e2 at a non-identity pose."""
+    target = ds.make_urban_slab(20000, seed=21)
+    scan = ds.perturb_scan(target, seed=4)
+    T = T_nonid()
+    tg = orc.build_target(method, target, max_dist=2.0, k=10)
+    H, g, e2, n_in = orc.linearize(tg, T, scan)
+    moved = np.ascontiguousarray(orc.transform_scan_f32(T, scan))
+    gh = hs.hs_grid_build(ptr(target), len(target), 0.4)
+    assert hs.hs_shell_build(gh, 2.0) >= len(target)
+    idx = np.empty(len(moved), np.int64); dist = np.empty(len(moved), np.float32); used = np.zeros(len(moved), np.uint8)
+    hs.hs_shell_nn(gh, ptr(moved), len(moved), 2.0, ptr(idx), ptr(dist), ptr(used), 0)
+    hs.hs_grid_free(gh)
+    ok = (idx >= 0).astype(np.uint8)
+    nn = np.where(idx >= 0, idx, 0)
+    recs = np.zeros((len(scan), 9), dtype=np.float32)
+    recs[:, :3] = tg.points[nn]
+    if method == orc.PLANE:
+        recs[:, 3:6] = tg.normals[nn]
+    out = np.zeros(29)
+    Tc = np.ascontiguousarray(T)
+    hs.hs_linearize(method, ptr(Tc), ptr(scan), len(scan), ptr(recs), ptr(ok), ptr(out))
+    Hm = np.zeros((6, 6))
+    Hm[np.triu_indices(6)] = out[:21]
+    Hm = Hm + np.triu(Hm, 1).T
+    assert int(out[28]) == n_in
+    assert rel_err(Hm, H) < 2e-5
+    assert np.max(np.abs(out[21:27] - g)) < 2e-5 * max(np.max(np.abs(g)), np.sqrt(np.max(np.abs(H)) * e2))
+    assert abs(out[27] - e2) < 2e-5 * e2
+
+
 def test_small_linalg(hs):
     rng = np.random.default_rng(5)
     for scale in (1.0, 0.1, 3e-3, 1e-3, 1e-5):
