@@ -120,7 +120,8 @@ int pcr_set_scan_posed(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, cons
 /* ---- per iteration --------------------------------------------------------------------- */
 
 /* One linearisation at transform T: SE(3) transform of the scan, exact correspondence
- * search, residual + Jacobian, reduction to the normal equations -- one fused kernel.
+ * search, residual + Jacobian, reduction to the normal equations -- one fused kernel on the
+ * default (tile stream) path, a correspondence and an accumulate kernel on the list path.
  * Replaces ICP/PlaneICP/VPlaneICP/NDT.calc_H_g_e2 (icp.py:24, plane_icp.py:30,
  * voxelized_plane_icp.py:23, ndt.py:24).  With a communicator attached (pcr_comm_init_rank)
  * the record is summed over all ranks before it is returned. */
@@ -196,6 +197,20 @@ int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
  * PCR_SHELL_LISTS=0 / PCR_SHELL_DMAX / PCR_SHELL_MAX_GIB tune the build. */
 int pcr_set_shell_lists(pcr_ctx* ctx, int enable);
 int pcr_shell_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries, double* margin_cells);
+/* Which implementation of the per-iteration path runs (both exact, same results up to float64
+ * summation order): 0 = tile stream (default): one fused kernel per linearisation; every warp
+ * stages the cell box around its 32 scan points from a row-major dense grid into shared memory with
+ * cp.async.bulk and searches it there (csrc/pcr_tile.cuh, pcr_tile_kernel.cuh); 1 = round-1 list
+ * kernels (shell lists / voxel candidate lists + separate accumulate kernel), kept for A/B.
+ * Structures are built for the path that is selected when set_target runs: choose it right after
+ * pcr_create (or with PCR_PATH=lists in the environment). */
+int pcr_set_path(pcr_ctx* ctx, int path);
+/* Row grid of the tile-stream path (which: 0 target points, 1 kept voxel means): cell edge, number
+ * of cells of the dense table, occupied cells, bytes of the whole structure. */
+int pcr_tile_stats(pcr_ctx* ctx, int which, double* cell_edge, int64_t* cells, int64_t* occupied, int64_t* bytes);
+/* 1: every linearisation also parks the matched positions for pcr_debug_matches (4 B per scan
+ * point of extra traffic on the tile-stream path; the list kernels always park them). */
+int pcr_set_record_matches(pcr_ctx* ctx, int enable);
 /* Test hook: correspondences parked by the LAST linearisation (any search variant): per resident
  * scan point, in storage order (upload with sort <= 0 to keep the caller's order), the caller
  * index of the matched target point (which = 0) / kept voxel (which = 1) or -1. */

@@ -62,6 +62,9 @@ SYMBOLS = {
     "pcr_set_voxel_lists": (_i, [_vp, _i]),
     "pcr_voxel_list_stats": (_i, [_vp, _pi64, _pi64]),
     "pcr_index_stats": (_i, [_vp, _i, C.POINTER(_d), _pi64, _pi64, _pi64]),
+    "pcr_set_path": (_i, [_vp, _i]),
+    "pcr_tile_stats": (_i, [_vp, _i, C.POINTER(_d), _pi64, _pi64, _pi64]),
+    "pcr_set_record_matches": (_i, [_vp, _i]),
 }
 
 
@@ -261,6 +264,18 @@ class Context:
         a, b, m = C.c_int64(), C.c_int64(), C.c_double()
         self._check(self._lib.pcr_shell_list_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
         return dict(band_cells=a.value, entries=b.value, margin_cells=m.value, bytes=b.value * 17)
+
+    def set_path(self, path):
+        """'tile' (default) or 'lists' (round-1 kernels); call before set_target builds its structures."""
+        self._check(self._lib.pcr_set_path(self._h, {"tile": 0, "lists": 1}[path] if isinstance(path, str) else int(path)))
+
+    def set_record_matches(self, enable):
+        self._check(self._lib.pcr_set_record_matches(self._h, int(bool(enable))))
+
+    def tile_stats(self, which=0):
+        h, nc, no, nb = C.c_double(), C.c_int64(), C.c_int64(), C.c_int64()
+        self._check(self._lib.pcr_tile_stats(self._h, int(which), C.byref(h), C.byref(nc), C.byref(no), C.byref(nb)))
+        return dict(cell_edge=h.value, cells=nc.value, occupied=no.value, bytes=nb.value)
 
     def debug_matches(self, n_scan, which=0):
         """Caller indices matched by the last linearisation, per resident scan point (storage order)."""

@@ -987,6 +987,7 @@ static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     ctx->has_voxels = false; ctx->has_icov = false;
     ctx->vox_grid_epoch++;
     ctx->vox_grid.release();
+    ctx->tile_vox.release();
     ctx->n_vox = n_keep; ctx->n_vox_all = F.n_seg; ctx->voxel_size = voxel_size;
     const size_t nk = n_keep ? n_keep : 1;
     PCR_CUDA(ctx->vox_mean.ensure(nk * 3 * 8));
@@ -1030,10 +1031,246 @@ static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     g.built = true;
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     F.release();
-    rc = build_voxel_lists(ctx);
+    if (ctx->use_tile) rc = ensure_tile_index(ctx, PCR_VPLANE);   // row grid over the kept means + both payloads
+    else rc = build_voxel_lists(ctx);
     if (rc) return rc;
     ctx->has_voxels = true;
     ctx->has_icov = with_icov != 0;
+    return PCR_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// row grid + row-major point copy for the tile-stream kernel (pcr_tile.cuh)
+// ---------------------------------------------------------------------------------------
+__global__ void bbox4_kernel(const float4* __restrict__ pts, long long n, int* __restrict__ mm) {
+    int lo[3] = {INT_MAX, INT_MAX, INT_MAX}, hi[3] = {INT_MIN, INT_MIN, INT_MIN};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float4 p = pts[i];
+        if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+            int a = f2ord(p.x), b = f2ord(p.y), c = f2ord(p.z);
+            lo[0] = min(lo[0], a); hi[0] = max(hi[0], a);
+            lo[1] = min(lo[1], b); hi[1] = max(hi[1], b);
+            lo[2] = min(lo[2], c); hi[2] = max(hi[2], c);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = min(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = max(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { atomicMin(&mm[a], lo[a]); atomicMax(&mm[3 + a], hi[a]); }
+    }
+}
+
+// cell number (x fastest) of every source point + histogram of the cells
+__global__ void tile_key_kernel(const float4* __restrict__ src, long long n, TileGrid G, uint32_t* __restrict__ keys,
+                                uint32_t* __restrict__ vals, uint32_t* __restrict__ hist) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = src[i];
+    float gx = (p.x - G.ox) * G.inv_c, gy = (p.y - G.oy) * G.inv_c, gz = (p.z - G.oz) * G.inv_c;
+    if (!(gx == gx)) gx = 0.f;
+    if (!(gy == gy)) gy = 0.f;
+    if (!(gz == gz)) gz = 0.f;
+    const float big = 1.0e9f;
+    const int cx = cell_of(fminf(fmaxf(gx, -big), big), G.nx);
+    const int cy = cell_of(fminf(fmaxf(gy, -big), big), G.ny);
+    const int cz = cell_of(fminf(fmaxf(gz, -big), big), G.nz);
+    const uint32_t key = (uint32_t)(((size_t)cz * G.ny + cy) * G.nx + cx);
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
+    atomicAdd(&hist[key], 1u);
+}
+
+__global__ void tile_count_occupied_kernel(const uint32_t* __restrict__ hist, unsigned long long ncells, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < ncells; i += (unsigned long long)gridDim.x * blockDim.x)
+        c += hist[i] != 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+__global__ void tile_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ vals, long long n,
+                                   float4* __restrict__ pts, uint32_t* __restrict__ perm) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = vals[i];
+    const float4 p = src[j];
+    pts[i] = make_float4(p.x, p.y, p.z, __uint_as_float((uint32_t)i));
+    perm[i] = j;
+}
+
+// payload in row-grid order: mode 0 = one float4 per source point (normals in source order);
+// mode 1 = VPlaneICP record (2 float4 / voxel: mean, normal) -> normal; mode 2 = NDT record
+// (3 float4 / voxel: (mean, W00), (W01, W02, W11, W12), (W22, ..)) -> (W00, W01, W02, W11), (W12, W22, 0, 0)
+__global__ void tile_payload_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ perm, long long n, int mode,
+                                    float4* __restrict__ pay) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t j = perm[i];
+    if (mode == 0) {
+        pay[i] = src[j];
+    } else if (mode == 1) {
+        pay[i] = src[2 * j + 1];
+    } else {
+        const float4 a = src[3 * j], b = src[3 * j + 1], c = src[3 * j + 2];
+        pay[2 * i] = make_float4(a.w, b.x, b.y, b.z);
+        pay[2 * i + 1] = make_float4(b.w, c.x, 0.f, 0.f);
+    }
+}
+
+constexpr unsigned long long kMaxTileCells = 1ull << 29;   // 2 GiB of cell starts
+
+// Build the row grid over n float4 source points (xyz + anything); ppc = desired mean points per
+// occupied cell.  out.perm maps a position of the new order to the index in `src`.
+static int build_tile_index(pcr_ctx* ctx, const float4* src, long long n, double ppc, TileIndex& out) {
+    out.release();
+    TileGrid V{};
+    if (n <= 0) {
+        // empty index (e.g. no voxel survived min_points): one empty cell, every query misses
+        V.ox = V.oy = V.oz = 0.f; V.c = 1.f; V.inv_c = 1.f; V.inv_c2 = 1.f; V.slack = 1e-3f;
+        V.nx = V.ny = V.nz = 1; V.n = 0;
+        PCR_CUDA(out.cs.ensure(2 * 4));
+        PCR_CUDA(cudaMemsetAsync(out.cs.p, 0, 8, ctx->stream));
+        PCR_CUDA(out.pts.ensure(16));
+        PCR_CUDA(out.perm.ensure(4));
+        V.cs = out.cs.as<uint32_t>(); V.pts = out.pts.as<float4>();
+        out.view = V; out.built = true; out.n_cells_occupied = 0;
+        return PCR_OK;
+    }
+    if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "point count exceeds 2^31-1");
+    PCR_CUDA(ctx->tmp_e.ensure(64));
+    int* d_mm = ctx->tmp_e.as<int>();
+    init_minmax_kernel<<<1, 32, 0, ctx->stream>>>(d_mm);
+    PCR_LAUNCH_CHECK();
+    bbox4_kernel<<<min(blocks_for(n, 256), ctx->sm_count * 8), 256, 0, ctx->stream>>>(src, n, d_mm);
+    PCR_LAUNCH_CHECK();
+    int h_mm[6];
+    PCR_CUDA(cudaMemcpyAsync(h_mm, d_mm, sizeof(h_mm), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_mm[0] == INT_MAX) return fail(ctx, PCR_ERR_ARG, "point set has no finite points");
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = ord2f_host(h_mm[a]); hi[a] = ord2f_host(h_mm[3 + a]); }
+    double ext[3], maxext = 0, maxabs = 0;
+    for (int a = 0; a < 3; ++a) {
+        ext[a] = (double)hi[a] - (double)lo[a];
+        maxext = std::max(maxext, ext[a]);
+        maxabs = std::max(maxabs, std::max(fabs((double)lo[a]), fabs((double)hi[a])));
+    }
+    if (maxext <= 0) maxext = 1.0;
+    double vol = 1.0;
+    for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * maxext);
+    double c = cbrt(vol * ppc / (double)n);
+    c = std::max(c, maxext * 1e-5);
+
+    PCR_CUDA(ctx->tmp_a.ensure((size_t)n * 8));
+    PCR_CUDA(ctx->tmp_b.ensure((size_t)n * 8));
+    uint32_t* k_in = ctx->tmp_a.as<uint32_t>(); uint32_t* k_out = k_in + n;
+    uint32_t* v_in = ctx->tmp_b.as<uint32_t>(); uint32_t* v_out = v_in + n;
+    const int max_attempts = 4;
+    for (int attempt = 0; attempt < max_attempts; ++attempt) {
+        unsigned long long ncells;
+        for (;;) {   // enlarge the cell until the dense table fits
+            V.c = (float)c; V.inv_c = (float)(1.0 / c); V.inv_c2 = V.inv_c * V.inv_c;
+            // one and a half empty cells around the bounding box: no indexed point is ever clamped into a border cell
+            V.ox = lo[0] - 1.5f * V.c; V.oy = lo[1] - 1.5f * V.c; V.oz = lo[2] - 1.5f * V.c;
+            double d[3];
+            for (int a = 0; a < 3; ++a) d[a] = floor(((double)hi[a] - (double)(lo[a] - 1.5f * V.c)) / c) + 3.0;
+            if (d[0] < 2.0e6 && d[1] < 2.0e6 && d[2] < 2.0e6 && d[0] * d[1] * d[2] <= (double)kMaxTileCells) {
+                V.nx = (int)d[0]; V.ny = (int)d[1]; V.nz = (int)d[2];
+                break;
+            }
+            c *= 1.2599210498948732;
+        }
+        ncells = (unsigned long long)V.nx * V.ny * V.nz;
+        V.slack = 1e-3f + 1e-6f * (float)(2.0 * maxabs / c + (double)std::max(V.nx, std::max(V.ny, V.nz)));
+        V.n = (uint32_t)n;
+        PCR_CUDA(out.cs.ensure((size_t)(ncells + 1) * 4));
+        PCR_CUDA(cudaMemsetAsync(out.cs.p, 0, (size_t)(ncells + 1) * 4, ctx->stream));
+        PCR_CUDA(ctx->tile_scratch.ensure(64));
+        PCR_CUDA(cudaMemsetAsync(ctx->tile_scratch.p, 0, 64, ctx->stream));
+        tile_key_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(src, n, V, k_in, v_in, out.cs.as<uint32_t>());
+        PCR_LAUNCH_CHECK();
+        tile_count_occupied_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(out.cs.as<uint32_t>(), ncells, ctx->tile_scratch.as<unsigned long long>());
+        PCR_LAUNCH_CHECK();
+        unsigned long long occ = 0;
+        PCR_CUDA(cudaMemcpyAsync(&occ, ctx->tile_scratch.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        const double got = (double)n / (double)std::max<unsigned long long>(occ, 1ull);
+        if (attempt + 1 < max_attempts && (got > 1.6 * ppc || (got < ppc / 1.6 && occ > 64))) {
+            double ratio = sqrt(ppc / got);                 // points lie on 2-D surfaces: ppc ~ c^2
+            ratio = std::min(std::max(ratio, 0.25), 4.0);
+            c *= ratio;
+            continue;
+        }
+        out.n_cells_occupied = (long long)occ;
+        // ---- accept: sort by cell number, cell starts = exclusive prefix sum of the histogram ----
+        size_t tmp = 0;
+        const int end_bit = bits_for(ncells);
+        PCR_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp, k_in, k_out, v_in, v_out, n, 0, end_bit, ctx->stream));
+        PCR_CUDA(ctx->cub_tmp.ensure(tmp));
+        PCR_CUDA(cub::DeviceRadixSort::SortPairs(ctx->cub_tmp.p, tmp, k_in, k_out, v_in, v_out, n, 0, end_bit, ctx->stream));
+        ctx->launches += 4;
+        int rc = exclusive_sum_u32(ctx, out.cs.as<uint32_t>(), out.cs.as<uint32_t>(), (long long)(ncells + 1));
+        if (rc) return rc;
+        PCR_CUDA(out.pts.ensure((size_t)n * sizeof(float4)));
+        PCR_CUDA(out.perm.ensure((size_t)n * 4));
+        tile_gather_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(src, v_out, n, out.pts.as<float4>(), out.perm.as<uint32_t>());
+        PCR_LAUNCH_CHECK();
+        V.cs = out.cs.as<uint32_t>();
+        V.pts = out.pts.as<float4>();
+        out.view = V;
+        out.built = true;
+        PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        return PCR_OK;
+    }
+    return fail(ctx, PCR_ERR_LIMIT, "row grid build did not converge");
+}
+
+static int build_tile_payload(pcr_ctx* ctx, TileIndex& t, const float4* src, int mode, DevBuf& pay) {
+    const long long n = t.view.n;
+    const size_t per = mode == 2 ? 2 : 1;
+    PCR_CUDA(pay.ensure(std::max<size_t>((size_t)n * per, 1) * sizeof(float4)));
+    if (n > 0) {
+        tile_payload_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(src, t.perm.as<uint32_t>(), n, mode, pay.as<float4>());
+        PCR_LAUNCH_CHECK();
+    }
+    return PCR_OK;
+}
+
+// Build / refresh what the tile-stream kernel needs for `method` (called by the set_target entry
+// points and, as a safety net, by the first linearisation).
+int ensure_tile_index(pcr_ctx* ctx, int method) {
+    if (method == PCR_ICP || method == PCR_PLANE) {
+        if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "row grid: target NN index not built");
+        if (!ctx->tile_tgt.built) {
+            int rc = build_tile_index(ctx, ctx->tgt_grid.view.pts, ctx->n_tgt, ctx->tile_ppc_tgt, ctx->tile_tgt);
+            if (rc) return rc;
+        }
+        if (method == PCR_PLANE && ctx->has_normals && ctx->tile_tgt.pay_epoch != ctx->normals_epoch) {
+            int rc = build_tile_payload(ctx, ctx->tile_tgt, ctx->tgt_nrm_sorted.as<float4>(), 0, ctx->tile_tgt.pay);
+            if (rc) return rc;
+            ctx->tile_tgt.pay_epoch = ctx->normals_epoch;
+            PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    } else {
+        if (!ctx->vox_grid.built) return fail(ctx, PCR_ERR_STATE, "row grid: voxels not built");
+        if (!ctx->tile_vox.built) {
+            int rc = build_tile_index(ctx, ctx->vox_grid.view.pts, ctx->n_vox, ctx->tile_ppc_vox, ctx->tile_vox);
+            if (rc) return rc;
+            rc = build_tile_payload(ctx, ctx->tile_vox, ctx->vox_rec_plane.as<float4>(), 1, ctx->tile_vox.pay);
+            if (rc) return rc;
+            rc = build_tile_payload(ctx, ctx->tile_vox, ctx->vox_rec_ndt.as<float4>(), 2, ctx->tile_vox.pay2);
+            if (rc) return rc;
+            PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
     return PCR_OK;
 }
 
@@ -1143,6 +1380,15 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_CELL_ORDER")) ctx->cell_order = atoi(e) != 0;
     if (const char* e = getenv("PCR_GRAB_ROWS")) ctx->grab_rows = atoi(e) >= 0 && atoi(e) <= 64 ? atoi(e) : 0;
     if (const char* e = getenv("PCR_SPLIT")) ctx->split_passes = atoi(e) != 0;
+    if (const char* e = getenv("PCR_PATH")) ctx->use_tile = strcmp(e, "lists") != 0;
+    if (const char* e = getenv("PCR_TILE_PPC")) ctx->tile_ppc_tgt = atof(e) > 0.25 ? atof(e) : 8.0;
+    if (const char* e = getenv("PCR_TILE_PPC_VOX")) ctx->tile_ppc_vox = atof(e) > 0.25 ? atof(e) : 4.0;
+    if (const char* e = getenv("PCR_TILE_CAP")) ctx->tile_cap = atoi(e) >= 256 && atoi(e) <= 4096 ? atoi(e) / 4 * 4 : 256;
+    if (const char* e = getenv("PCR_TILE_CSCAP")) ctx->tile_cscap = atoi(e) >= 64 && atoi(e) <= 8192 ? atoi(e) : 512;
+    if (const char* e = getenv("PCR_TILE_CORE")) ctx->tile_core_e = atoi(e) >= 0 && atoi(e) <= 16 ? atoi(e) : 8;
+    if (const char* e = getenv("PCR_TILE_MINB")) ctx->tile_min_blocks = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 0;
+    if (const char* e = getenv("PCR_TILE_R0")) ctx->tile_first_radius = atof(e) > 0.0 ? (float)atof(e) : 0.5f;
+    if (const char* e = getenv("PCR_TILE_KR")) ctx->tile_rows_per_unit = atoi(e) == 2 || atoi(e) == 4 ? atoi(e) : 0;
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
     *out = ctx;
@@ -1160,6 +1406,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release();
     ctx->shell_bricks.release(); ctx->shell_start.release(); ctx->shell_pts.release(); ctx->shell_margin2.release();
     ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();
+    ctx->tile_tgt.release(); ctx->tile_vox.release(); ctx->scan_hint.release(); ctx->tile_scratch.release();
     ctx->partials.release(); ctx->state.release();
     ctx->tmp_a.release(); ctx->tmp_b.release(); ctx->tmp_c.release(); ctx->tmp_d.release(); ctx->tmp_e.release(); ctx->cub_tmp.release();
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
@@ -1177,6 +1424,7 @@ int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n) {
     if (!xyz || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_set_target_points: empty target");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->tgt_grid.release();
+    ctx->tile_tgt.release();
     ctx->tgt_shell = ShellLists{};              // lists refer to the released grid
     ctx->n_shell_band = ctx->n_shell_entries = 0;
     ctx->shell_tried = false;
@@ -1194,6 +1442,7 @@ int pcr_build_nn_index(pcr_ctx* ctx) {
     if (ctx->n_tgt <= 0) return fail(ctx, PCR_ERR_STATE, "pcr_build_nn_index: target points not set");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->tgt_grid_epoch++;
+    ctx->tile_tgt.release();
     ctx->tgt_shell = ShellLists{};              // lists of the previous grid are void; rebuilt on demand
     ctx->n_shell_band = ctx->n_shell_entries = 0;
     ctx->shell_dmax_used = 0.0;
@@ -1206,6 +1455,7 @@ int pcr_build_correspondence_lists(pcr_ctx* ctx) {
     if (!ctx->tgt_grid.built) return fail(ctx, PCR_ERR_STATE, "pcr_build_correspondence_lists: NN index not built");
     PCR_CUDA(cudaSetDevice(ctx->device));
     ctx->shell_tried = true;
+    if (ctx->use_tile) return ensure_tile_index(ctx, ctx->has_normals ? PCR_PLANE : PCR_ICP);   // row grid (+ normals in its order)
     return build_shell_lists(ctx);
 }
 
@@ -1230,6 +1480,8 @@ int pcr_estimate_normals(pcr_ctx* ctx, int k) {
     PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->has_normals = true;
+    ctx->normals_epoch++;
+    if (ctx->use_tile && ctx->tile_tgt.built) return ensure_tile_index(ctx, PCR_PLANE);
     return PCR_OK;
 }
 
@@ -1252,6 +1504,8 @@ int pcr_set_normals(pcr_ctx* ctx, const float* normals) {
     PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->has_normals = true;
+    ctx->normals_epoch++;
+    if (ctx->use_tile && ctx->tile_tgt.built) return ensure_tile_index(ctx, PCR_PLANE);
     return PCR_OK;
 }
 
@@ -1409,6 +1663,30 @@ int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries) {
     if (!ctx) return PCR_ERR_ARG;
     if (band_cells) *band_cells = ctx->n_band_cells;
     if (entries) *entries = ctx->n_list_entries;
+    return PCR_OK;
+}
+
+int pcr_set_path(pcr_ctx* ctx, int path) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (path != 0 && path != 1) return fail(ctx, PCR_ERR_ARG, "pcr_set_path: 0 = tile stream, 1 = lists");
+    ctx->use_tile = path == 0;
+    return PCR_OK;
+}
+
+int pcr_set_record_matches(pcr_ctx* ctx, int enable) {
+    if (!ctx) return PCR_ERR_ARG;
+    ctx->record_matches = enable ? 1 : 0;
+    return PCR_OK;
+}
+
+int pcr_tile_stats(pcr_ctx* ctx, int which, double* cell_edge, int64_t* cells, int64_t* occupied, int64_t* bytes) {
+    if (!ctx) return PCR_ERR_ARG;
+    const TileIndex& t = which == 0 ? ctx->tile_tgt : ctx->tile_vox;
+    if (!t.built) return fail(ctx, PCR_ERR_STATE, "pcr_tile_stats: row grid not built");
+    if (cell_edge) *cell_edge = t.view.c;
+    if (cells) *cells = (int64_t)t.view.nx * t.view.ny * t.view.nz;
+    if (occupied) *occupied = t.n_cells_occupied;
+    if (bytes) *bytes = (int64_t)(t.cs.bytes + t.pts.bytes + t.perm.bytes + t.pay.bytes + t.pay2.bytes);
     return PCR_OK;
 }
 

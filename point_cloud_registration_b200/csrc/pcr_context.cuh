@@ -8,6 +8,7 @@
 
 #include "../../include/pcr_b200.h"
 #include "pcr_common.cuh"
+#include "pcr_tile.cuh"
 
 #ifndef PCR_ACC_BATCH
 #define PCR_ACC_BATCH 2
@@ -63,6 +64,17 @@ struct Grid {
     void release() { bricks.release(); cell_start.release(); pts.release(); built = false; n_cells = 0; }
 };
 
+// Row grid + row-major point copy the tile-stream kernel stages from (see pcr_tile.cuh).
+struct TileIndex {
+    TileGrid view{};
+    DevBuf cs, pts, perm;     // cell starts, points (x, y, z, own position), position -> position in the source index
+    DevBuf pay, pay2;         // per-point payload in the same order: normals (PlaneICP / VPlaneICP); NDT inverse covariances
+    long long n_cells_occupied = 0;
+    long long pay_epoch = -1;
+    bool built = false;
+    void release() { cs.release(); pts.release(); perm.release(); pay.release(); pay2.release(); built = false; pay_epoch = -1; }
+};
+
 }  // namespace pcr
 
 struct pcr_ctx {
@@ -103,6 +115,23 @@ struct pcr_ctx {
     pcr::DevBuf vox_rec_ndt;      // float4[3n]: (mean, W00), (W01, W02, W11, W12), (W22, 0, 0, 0)
     bool has_voxels = false, has_icov = false;
 
+    // ---- tile-stream path (default hot path; see pcr_tile.cuh) ----
+    pcr::TileIndex tile_tgt;      // over the target points (ICP / PlaneICP)
+    pcr::TileIndex tile_vox;      // over the kept voxel means (VPlaneICP / NDT)
+    int use_tile = 1;             // 1: tile-stream kernel, 0: round-1 list kernels (A/B, PCR_PATH=lists)
+    double tile_ppc_tgt = 8.0;    // desired mean points per occupied cell of the row grids
+    double tile_ppc_vox = 4.0;
+    int tile_cap = 256;           // points a warp can stage at once
+    int tile_cscap = 512;         // cell-start words a warp can stage at once
+    int tile_core_e = 8;          // lanes farther than this many cells from the leader wait for their own pass
+    int tile_min_blocks = 0;      // resident blocks per SM requested (0: default)
+    int tile_rows_per_unit = 0;   // warp rows per unit of work (2 or 4; 0: chosen from the scan size)
+    int record_matches = 0;       // 1: the tile kernel also parks the matched positions (pcr_debug_matches)
+    long long normals_epoch = 0;
+    float tile_first_radius = 0.5f;   // halo radius (cells) a new scan starts with
+    pcr::DevBuf scan_hint;        // float[n_pad / 32]: halo radius each warp row needed last time
+    pcr::DevBuf tile_scratch;     // histogram / counters of the row-grid build
+
     // ---- scan ----
     long long n_scan = 0;         // real points
     long long n_scan_pad = 0;     // padded to a multiple of 32 with NaN (whole tiles enter the kernel loop)
@@ -114,7 +143,7 @@ struct pcr_ctx {
     int cell_order = 1;           // scan upload: order by correspondence-grid cell (0: Morton order in the scan's frame)
     int grab_rows = 0;            // rows of 32 scan slots a warp fetches at a time (0: chosen from the scan size)
     int split_passes = 1;         // 1: correspond + accumulate kernels, 0: one fused kernel (A/B)
-    int lin_blocks_per_sm[4][9] = {};   // cached occupancy per (method, kernel variant)
+    int lin_blocks_per_sm[4][12] = {};   // cached occupancy per (method, kernel variant)
     pcr::DevBuf scan_x, scan_y, scan_z;
     pcr::DevBuf scan_prev;        // int[n_pad]: position matched by the previous linearisation (warm start)
     int prev_which = -1;          // index the positions refer to (0 target grid, 1 voxel grid, -1 none)
@@ -178,6 +207,7 @@ inline bool is_device_pointer(const void* p) {
 
 // internal cross-TU entry points
 int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, DevBuf* sorted_payload_out);
+int ensure_tile_index(pcr_ctx* ctx, int method);   // builds / refreshes the row grid + payload the method needs
 int ensure_loop_buffers(pcr_ctx* ctx);
 
 }  // namespace pcr

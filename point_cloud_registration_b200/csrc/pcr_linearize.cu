@@ -99,8 +99,18 @@ __device__ __forceinline__ void accumulate_match(const Pose32& pose, float* acc,
 }
 
 // Last block only, one thread: assemble the record, publish it, optionally do the GN step.
+// (Out of line, and fed a small by-value parameter block: taking the address of the kernel's
+// parameter struct would copy all of it to local memory at the start of every thread.)
+struct FinishParams {
+    LoopState* st;
+    double* out_mapped;
+    double tol;
+    int device_loop;
+    int max_iter;
+};
+
 template <int METHOD>
-__device__ __noinline__ void finish_iteration(const LinParams& P, BlockShared& sh) {
+__device__ __noinline__ void finish_iteration(const FinishParams P, BlockShared& sh) {
     LoopState* st = P.st;
     double rec[PCR_NEQ_PAD];
     if (METHOD == PCR_METHOD_ICP) {
@@ -142,19 +152,13 @@ __device__ __noinline__ void finish_iteration(const LinParams& P, BlockShared& s
 
 // float32 per-thread sums -> float64 warp shuffles -> shared memory -> per-block partial ->
 // the last block to arrive reduces all partials in a fixed order and finishes the iteration.
+// second half of the reduction: sh.red[warp][term] holds the float64 sums of every warp (the
+// caller has synchronised the block) -> per-block partial -> last block finishes the iteration
 template <int METHOD>
-__device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShared& sh, const float* acc) {
+__device__ __forceinline__ void block_finish(const LinParams& P, BlockShared& sh) {
     constexpr int NRED = NAcc<METHOD>::value;
     constexpr int NWARP = kLinThreads / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int i = 0; i < NRED; ++i) {
-        double v = (double)acc[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-        if (lane == 0) sh.red[warp][i] = v;
-    }
-    __syncthreads();
     if (threadIdx.x < NRED) {
         double v = 0.0;
 #pragma unroll
@@ -178,7 +182,26 @@ __device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShare
         if (lane == 0) sh.sum[i] = v;
     }
     __syncthreads();
-    if (threadIdx.x == 0) finish_iteration<METHOD>(P, sh);
+    if (threadIdx.x == 0) {
+        FinishParams F;
+        F.st = P.st; F.out_mapped = P.out_mapped; F.tol = P.tol; F.device_loop = P.device_loop; F.max_iter = P.max_iter;
+        finish_iteration<METHOD>(F, sh);
+    }
+}
+
+template <int METHOD>
+__device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShared& sh, const float* acc) {
+    constexpr int NRED = NAcc<METHOD>::value;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NRED; ++i) {
+        double v = (double)acc[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if (lane == 0) sh.red[warp][i] = v;
+    }
+    __syncthreads();
+    block_finish<METHOD>(P, sh);
 }
 
 __device__ __forceinline__ bool load_pose(const LinParams& P, BlockShared& sh, Pose32& pose) {
@@ -328,6 +351,10 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_fused_kernel(cons
     accumulate_pass<METHOD>(P, sh, pose);
 }
 
+}  // namespace pcr
+#include "pcr_tile_kernel.cuh"
+namespace pcr {
+
 __global__ void matches_kernel(const int* __restrict__ prev, const float4* __restrict__ pts, long long n, long long* __restrict__ idx) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -356,6 +383,11 @@ __global__ void gn_step_kernel(LoopState* st, double tol, int max_iter) {
     st->dx_norm = dxn;
     st->iter = iter;
     st->done = done;
+}
+
+__global__ void fill_float_kernel(float* p, long long n, float v) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
 }
 
 struct T16 { double v[16]; };
@@ -630,7 +662,75 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     return PCR_OK;
 }
 
+// ---- tile-stream path -------------------------------------------------------------------------
+template <int METHOD, int MINB, int KR>
+static int launch_tile_kernel(pcr_ctx* ctx, const LinParams& P, const TileParams& TP, int& cached_blocks) {
+    const size_t smem = (size_t)TP.warp_bytes * (kLinThreads / 32);
+    auto kernel = tile_linearize_kernel<METHOD, MINB, KR>;
+    if (cached_blocks == 0) {
+        PCR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kLinThreads, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+        cached_blocks = nb;
+    }
+    const long long rows = P.n_pad / 32;
+    long long want = (rows + kLinThreads / 32 - 1) / (kLinThreads / 32);
+    long long cap = (long long)ctx->sm_count * cached_blocks;
+    if (cap > kMaxLinBlocks) cap = kMaxLinBlocks;
+    if (want < 1) want = 1;
+    const int blocks = (int)(want < cap ? want : cap);
+    kernel<<<blocks, kLinThreads, smem, ctx->stream>>>(P, TP);
+    PCR_LAUNCH_CHECK();
+    return PCR_OK;
+}
+
+template <int METHOD>
+static int launch_tile(pcr_ctx* ctx, const LinParams& P) {
+    const bool vox = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
+    const TileIndex& t = vox ? ctx->tile_vox : ctx->tile_tgt;
+    TileParams TP{};
+    TP.G = t.view;
+    TP.pay = METHOD == PCR_METHOD_ICP ? nullptr : (METHOD == PCR_METHOD_NDT ? t.pay2.as<float4>() : t.pay.as<float4>());
+    TP.hint = ctx->scan_hint.as<float>();
+    TP.perm = t.perm.as<uint32_t>();
+    TP.match_out = ctx->record_matches ? ctx->scan_prev.as<int>() : nullptr;
+    TP.cap = ctx->tile_cap;
+    TP.cscap = ctx->tile_cscap;
+    TP.rmax = tile_rmax(t.view, P.max_d2);
+    TP.core_e = ctx->tile_core_e;
+    constexpr int KRMAX = 4;                       // match slots reserved per warp: [KRMAX][32] float4
+    TP.warp_bytes = (int)(((size_t)TP.cap * 16 + (size_t)TP.cscap * 4 + 16 + (size_t)KRMAX * 32 * 16 + 127) / 128 * 128);
+    int* cache = ctx->lin_blocks_per_sm[METHOD];
+    const int mb = ctx->tile_min_blocks > 0 ? ctx->tile_min_blocks : 3;
+    // rows per unit of work: 4 when every warp still gets many units, 2 for small scans (less tail)
+    const long long rows = P.n_pad / 32;
+    const bool big = ctx->tile_rows_per_unit > 0 ? ctx->tile_rows_per_unit >= 4 : rows >= (long long)ctx->sm_count * 32 * 4 * 8;
+    if (big) {
+        switch (mb) {
+            case 2: return launch_tile_kernel<METHOD, 2, 4>(ctx, P, TP, cache[9]);
+            case 3: return launch_tile_kernel<METHOD, 3, 4>(ctx, P, TP, cache[9]);
+            default: return launch_tile_kernel<METHOD, 4, 4>(ctx, P, TP, cache[9]);
+        }
+    }
+    switch (mb) {
+        case 2: return launch_tile_kernel<METHOD, 2, 2>(ctx, P, TP, cache[10]);
+        case 3: return launch_tile_kernel<METHOD, 3, 2>(ctx, P, TP, cache[10]);
+        default: return launch_tile_kernel<METHOD, 4, 2>(ctx, P, TP, cache[10]);
+    }
+}
+
 static int launch_linearize(pcr_ctx* ctx, int method, LinParams& P) {
+    if (ctx->use_tile) {
+        int rc = ensure_tile_index(ctx, method);
+        if (rc) return rc;
+        ctx->prev_which = ctx->record_matches ? ((method == PCR_ICP || method == PCR_PLANE) ? 0 : 1) : -1;
+        switch (method) {
+            case PCR_ICP: return launch_tile<PCR_METHOD_ICP>(ctx, P);
+            case PCR_PLANE: return launch_tile<PCR_METHOD_PLANE>(ctx, P);
+            case PCR_VPLANE: return launch_tile<PCR_METHOD_VPLANE>(ctx, P);
+            default: return launch_tile<PCR_METHOD_NDT>(ctx, P);
+        }
+    }
     // target-point methods stream shell lists: build them now if the caller did not (C-ABI users
     // that skipped pcr_build_correspondence_lists still get the fast path, one call late)
     if ((method == PCR_ICP || method == PCR_PLANE) && !ctx->shell_tried) {
@@ -701,11 +801,30 @@ static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, co
     PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
     PCR_CUDA(ctx->scan_prev.ensure(pad_bytes));
     ctx->prev_which = -1;                       // new scan: parked positions are void
+    PCR_CUDA(ctx->scan_hint.ensure((size_t)ctx->n_scan_pad / 32 * 4));
+    fill_float_kernel<<<(unsigned)((ctx->n_scan_pad / 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_hint.as<float>(), ctx->n_scan_pad / 32, ctx->tile_first_radius);
+    PCR_LAUNCH_CHECK();
     const uint32_t* order = nullptr;
     if (sort > 0 && n > 1) {
         // the grid the correspondences will be searched in, if it exists already
         const Grid* g = nullptr;
-        if ((method == PCR_VPLANE || method == PCR_NDT) && ctx->vox_grid.built && ctx->vox_grid.view.n_pts > 0) g = &ctx->vox_grid;
+        Grid tile_as_grid;                          // the row grid of the tile-stream path, described as a GridView for the key kernel
+        if (ctx->use_tile) {
+            const TileIndex* t = nullptr;
+            if ((method == PCR_VPLANE || method == PCR_NDT) && ctx->tile_vox.built && ctx->tile_vox.view.n > 0) t = &ctx->tile_vox;
+            else if ((method == PCR_ICP || method == PCR_PLANE || method < 0) && ctx->tile_tgt.built) t = &ctx->tile_tgt;
+            else if (method < 0 && ctx->tile_vox.built && ctx->tile_vox.view.n > 0) t = &ctx->tile_vox;
+            if (t) {
+                GridView& V = tile_as_grid.view;
+                V.ox = t->view.ox; V.oy = t->view.oy; V.oz = t->view.oz;
+                V.h = t->view.c; V.inv_h = t->view.inv_c;
+                V.cnx = t->view.nx; V.cny = t->view.ny; V.cnz = t->view.nz;
+                V.bnx = (V.cnx + 3) / 4; V.bny = (V.cny + 3) / 4; V.bnz = (V.cnz + 3) / 4;
+                g = &tile_as_grid;
+            }
+        }
+        if (g) {
+        } else if ((method == PCR_VPLANE || method == PCR_NDT) && ctx->vox_grid.built && ctx->vox_grid.view.n_pts > 0) g = &ctx->vox_grid;
         else if ((method == PCR_ICP || method == PCR_PLANE || method < 0) && ctx->tgt_grid.built) g = &ctx->tgt_grid;
         else if (method < 0 && ctx->vox_grid.built && ctx->vox_grid.view.n_pts > 0) g = &ctx->vox_grid;
         if (g && ctx->cell_order) {

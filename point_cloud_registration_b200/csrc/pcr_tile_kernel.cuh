@@ -1,0 +1,255 @@
+// Fused tile-stream linearisation kernel (sm_100a): the default hot path of libpcr_b200.so.
+// Included by pcr_linearize.cu (needs LinParams, BlockShared, MatchRec, accumulate_match,
+// finish_iteration, load_pose).
+//
+// One warp = one row of 32 consecutive scan points (cell-ordered on upload):
+//   coalesced SoA loads -> float32 SE(3) transform -> cell of every lane -> cell box of the row
+//   (+ halo) -> per (y,z) row of that box ONE bulk copy global -> shared (cp.async.bulk, completion
+//   on an mbarrier: SASS UBLKCP + SYNCS) of its contiguous point range, cell starts alongside ->
+//   every lane searches the staged box from shared memory (pcr_tile.cuh) -> settle test -> halo
+//   doubled for the lanes still open -> matched record gathered once -> residual + Jacobian terms
+//   in registers -> float64 reduction -> last block assembles the record and does the GN step.
+// No per-point list structure, no parked positions, no second kernel: compulsory traffic is the
+// scan, the staged target ranges (L2-resident between neighbouring rows) and one payload gather.
+#pragma once
+
+namespace pcr {
+
+constexpr float kTileMinRadius = 0.03125f;      // smallest halo radius (grid units) a row starts with
+
+struct TileParams {
+    TileGrid G;
+    const float4* pay;        // per indexed point: PLANE / VPLANE normal (1 float4), NDT (2 float4); null for ICP
+    float* hint;              // [n_pad / 32] halo radius (grid units) every warp row needed last time (first guess of this one)
+    const uint32_t* perm;     // position -> position in the source index (only for match_out)
+    int* match_out;           // optional [n_pad]: matched source position per scan slot (-1 none)
+    int cap;                  // points per warp stage buffer
+    int cscap;                // cell-start words per warp stage buffer
+    float rmax;               // halo radius at which every lane is settled by construction
+    int core_e;               // lanes farther than this many cells from the leader wait for their own pass
+    int warp_bytes;           // shared-memory stride between the stage buffers of two warps
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    const uint32_t a = smem_u32(bar);
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+    } while (!ok);
+}
+// 1-D bulk copy global -> shared through the TMA engine, bytes a multiple of 16, both sides 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// per-lane float32 sums of a few rows -> float64 totals, lane t keeps term t (fixed order: deterministic)
+template <int NACC>
+__device__ __forceinline__ void tile_flush(float* acc, double& acc64, float* scratch, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NACC; ++i) { scratch[i * 33 + lane] = acc[i]; acc[i] = 0.f; }
+    __syncwarp();
+    if (lane < NACC) {
+        double s = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) s += (double)scratch[lane * 33 + j];
+        acc64 += s;
+    }
+    __syncwarp();
+}
+
+// search half of one warp row: the matched point (x, y, z, position bits; position 0xffffffff = no
+// correspondence) of every lane is parked in shared memory for the accumulate half
+__device__ __forceinline__ void tile_search_row(const LinParams& P, const TileParams& TP, const Pose32* spose, long long row, int lane,
+                                                float4* spts, uint32_t* scs, uint64_t* bar, uint32_t& phase, float4* smatch) {
+    constexpr unsigned FULL = 0xffffffffu;
+    const TileGrid& G = TP.G;
+    const long long i = row * 32 + lane;
+    const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+    TileQuery q;
+    q.qx = q.qy = q.qz = q.gx = q.gy = q.gz = 0.f; q.ix = q.iy = q.iz = 0;
+    TileBest b;
+    b.d2 = P.max_d2; b.pos = kTileNone; b.x = b.y = b.z = 0.f;
+    bool valid = false;
+    if (px == px) {                                              // NaN = padding
+        float qx, qy, qz;
+        transform32(*spose, px, py, pz, qx, qy, qz);
+        valid = tile_make_query(G, qx, qy, qz, q) && !tile_query_far_outside(G, q, P.max_d2);
+    }
+    const float hint_in = TP.hint[row];
+    float rl = fminf(fmaxf(hint_in, kTileMinRadius), TP.rmax);   // this lane's halo radius (grid units)
+    unsigned todo = __ballot_sync(FULL, valid);
+    while (todo) {
+        // ---- one pass: leader = first open lane; everybody near it joins, the halo is the largest any of them asks for ----
+        const int leader = __ffs(todo) - 1;
+        const int lx = __shfl_sync(FULL, q.ix, leader), ly = __shfl_sync(FULL, q.iy, leader), lz = __shfl_sync(FULL, q.iz, leader);
+        const bool elig = ((todo >> lane) & 1u) && abs(q.ix - lx) <= TP.core_e && abs(q.iy - ly) <= TP.core_e && abs(q.iz - lz) <= TP.core_e;
+        const float rho = __int_as_float(__reduce_max_sync(FULL, elig ? __float_as_int(rl) : 0));   // radii are positive: bit order = value order
+        TileBox U;                                               // cells meeting [min - rho, max + rho] of the joined lanes (not clipped)
+        U.x0 = __reduce_min_sync(FULL, elig ? tile_cell_floor(q.gx - rho) : INT_MAX); U.x1 = __reduce_max_sync(FULL, elig ? tile_cell_floor(q.gx + rho) : INT_MIN);
+        U.y0 = __reduce_min_sync(FULL, elig ? tile_cell_floor(q.gy - rho) : INT_MAX); U.y1 = __reduce_max_sync(FULL, elig ? tile_cell_floor(q.gy + rho) : INT_MIN);
+        U.z0 = __reduce_min_sync(FULL, elig ? tile_cell_floor(q.gz - rho) : INT_MAX); U.z1 = __reduce_max_sync(FULL, elig ? tile_cell_floor(q.gz + rho) : INT_MIN);
+        TileBox R;                                               // the part of it inside the grid
+        R.x0 = max(U.x0, 0); R.x1 = min(U.x1, G.nx - 1);
+        R.y0 = max(U.y0, 0); R.y1 = min(U.y1, G.ny - 1);
+        R.z0 = max(U.z0, 0); R.z1 = min(U.z1, G.nz - 1);
+        if (R.x0 <= R.x1 && R.y0 <= R.y1 && R.z0 <= R.z1) {
+            const int rnx = R.x1 - R.x0 + 1, rny = R.y1 - R.y0 + 1, rnz = R.z1 - R.z0 + 1;
+            const int W = rnx + 1;
+            const int nrows = rny * rnz;
+            const int RB = min(32, TP.cscap / W);                // rows whose cell starts fit the stage buffer
+            int ra = 0;
+            while (ra < nrows) {
+                // ---- table pass: lane l looks up the point range of row ra + l ----
+                const int r = ra + lane;
+                const bool rowv = lane < RB && r < nrows;
+                uint32_t gs = 0u, ge = 0u;
+                size_t base = 0;
+                if (rowv) {
+                    const int jz = R.z0 + r / rny, jy = R.y0 + r % rny;
+                    base = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
+                    gs = __ldg(G.cs + base);
+                    ge = __ldg(G.cs + base + rnx);
+                }
+                const uint32_t len = ge - gs;
+                uint32_t incl = len;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += t;
+                }
+                const int nfit = __popc(__ballot_sync(FULL, rowv && incl <= (uint32_t)TP.cap));   // a prefix: incl is monotone
+                if (nfit == 0) {
+                    // row ra alone exceeds the stage buffer (or no cell-start room at all): search it in global memory
+                    const int jz = R.z0 + ra / rny, jy = R.y0 + ra % rny;
+                    const size_t gb = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
+                    if (elig) tile_visit_row(G, q, b, jy, jz, R.x0, R.x1, G.cs + gb, G.pts, INT_MIN);
+                    ra += 1;
+                    continue;
+                }
+                const uint32_t total = __shfl_sync(FULL, incl, nfit - 1);
+                if (total > 0u) {
+                    // ---- stage: one bulk copy per non-empty row, cell starts rebased to the stage buffer ----
+                    const uint32_t excl = incl - len;
+                    if (lane == 0) mbar_expect_tx(bar, total * 16u);
+                    __syncwarp();
+                    if (lane < nfit) {
+                        if (len) bulk_g2s(spts + excl, G.pts + gs, len * 16u, bar);
+                        const uint32_t bias = excl - gs;
+                        uint32_t* dst = scs + lane * W;
+                        for (int j = 0; j <= rnx; ++j) dst[j] = __ldg(G.cs + base + j) + bias;
+                    }
+                    __syncwarp();
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                    if (elig) {
+                        if (ra == 0 && nfit == nrows) tile_search_rings(G, q, b, R, ra, nfit, W, scs, spts);
+                        else tile_search_linear(G, q, b, R, ra, nfit, W, scs, spts);
+                    }
+                    __syncwarp();                                // everybody is done reading before the next stage overwrites
+                }
+                ra += nfit;
+            }
+        }
+        // ---- settle: final iff nothing outside the staged box can be closer; else ask for the ball of the
+        //      candidate (settles for certain next time) or, with no candidate yet, for twice the radius ----
+        bool settled = false;
+        if (elig) {
+            settled = rho >= TP.rmax || tile_settled(G, q, b, U);
+            if (!settled) rl = fminf(b.pos != kTileNone ? tile_radius_for(G, b) : fmaxf(2.0f * rho, 1.0f), TP.rmax);
+        }
+        todo &= ~__ballot_sync(FULL, settled);
+    }
+    smatch[lane] = make_float4(b.x, b.y, b.z, __uint_as_float(b.pos));
+    if (TP.match_out) TP.match_out[i] = b.pos != kTileNone ? (int)TP.perm[b.pos] : -1;
+    // first guess of the next linearisation: a little more than the farthest correspondence of this row
+    float need = b.pos != kTileNone ? sqrtf(b.d2) * G.inv_c : 0.0f;
+    need = __int_as_float(__reduce_max_sync(FULL, __float_as_int(need)));
+    need = need * 1.25f + 0.02f;
+    if (lane == 0 && need != hint_in) TP.hint[row] = need;
+}
+
+// accumulate half: matched record -> residual + Jacobian terms of this lane's correspondence
+template <int METHOD>
+__device__ __forceinline__ void tile_accumulate_row(const LinParams& P, const TileParams& TP, const Pose32* spose, long long row, int lane,
+                                                    const float4* smatch, float* acc) {
+    const float4 m = smatch[lane];
+    const uint32_t pos = __float_as_uint(m.w);
+    if (pos == kTileNone) return;
+    const long long i = row * 32 + lane;
+    MatchRec r;
+    r.a = make_float4(m.x, m.y, m.z, 0.f);
+    if (METHOD == PCR_METHOD_PLANE || METHOD == PCR_METHOD_VPLANE) {
+        r.b = __ldg(TP.pay + pos);
+    } else if (METHOD == PCR_METHOD_NDT) {
+        const float4 p0 = __ldg(TP.pay + 2 * (size_t)pos), p1 = __ldg(TP.pay + 2 * (size_t)pos + 1);
+        r.a.w = p0.x;
+        r.b = make_float4(p0.y, p0.z, p0.w, p1.x);
+        r.c = make_float4(p1.y, 0.f, 0.f, 0.f);
+    }
+    const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+    const Pose32 pose = *spose;
+    accumulate_match<METHOD>(pose, acc, r, px, py, pz);
+}
+
+// KR consecutive warp rows form one unit of work: their searches run first (the 29 accumulators are
+// dead meanwhile -- the search keeps its registers), then their terms are accumulated and flushed
+template <int METHOD, int MINB, int KR>
+__global__ void __launch_bounds__(kLinThreads, MINB) tile_linearize_kernel(const LinParams P, const TileParams TP) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ BlockShared sh;
+    __shared__ Pose32 spose;
+    constexpr int NACC = NAcc<METHOD>::value;
+    constexpr int NWARP = kLinThreads / 32;
+    {
+        Pose32 pose;
+        if (!load_pose(P, sh, pose)) return;
+        if (threadIdx.x == 0) spose = pose;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = tile_smem + (size_t)warp * TP.warp_bytes;
+    float4* spts = reinterpret_cast<float4*>(wbase);
+    uint32_t* scs = reinterpret_cast<uint32_t*>(wbase + (size_t)TP.cap * 16);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + (size_t)TP.cap * 16 + (size_t)TP.cscap * 4);
+    float4* smatch = reinterpret_cast<float4*>(wbase + (size_t)TP.cap * 16 + (size_t)TP.cscap * 4 + 16);   // [KR][32]
+    if (lane == 0) {
+        mbar_init(bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0u;
+    double acc64 = 0.0;
+    const long long rows = P.n_pad >> 5;
+    const long long groups = (rows + KR - 1) / KR;
+    const long long nwarps = (long long)gridDim.x * NWARP;
+    for (long long grp = (long long)blockIdx.x * NWARP + warp; grp < groups; grp += nwarps) {
+        const long long row0 = grp * KR;
+#pragma unroll 1
+        for (int u = 0; u < KR; ++u)
+            if (row0 + u < rows) tile_search_row(P, TP, &spose, row0 + u, lane, spts, scs, bar, phase, smatch + u * 32);
+        __syncwarp();
+        float acc[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) acc[k] = 0.f;
+#pragma unroll 1
+        for (int u = 0; u < KR; ++u)
+            if (row0 + u < rows) tile_accumulate_row<METHOD>(P, TP, &spose, row0 + u, lane, smatch + u * 32, acc);
+        tile_flush<NACC>(acc, acc64, reinterpret_cast<float*>(spts), lane);
+    }
+    if (lane < NACC) sh.red[warp][lane] = acc64;
+    __syncthreads();
+    block_finish<METHOD>(P, sh);
+}
+
+}  // namespace pcr

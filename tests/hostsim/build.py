@@ -9,7 +9,7 @@ SO = os.path.join(HERE, "_hostsim.so")
 def build(force=False):
     src = os.path.join(HERE, "hostsim.cu")
     deps = [src] + [os.path.join(HERE, "..", "..", "point_cloud_registration_b200", "csrc", f)
-                    for f in ("pcr_common.cuh", "pcr_grid.cuh", "pcr_linalg.cuh", "pcr_terms.cuh")]
+                    for f in ("pcr_common.cuh", "pcr_grid.cuh", "pcr_linalg.cuh", "pcr_terms.cuh", "pcr_tile.cuh")]
     if not force and os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in deps):
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

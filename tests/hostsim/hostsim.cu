@@ -12,6 +12,7 @@
 #include "../../point_cloud_registration_b200/csrc/pcr_grid.cuh"
 #include "../../point_cloud_registration_b200/csrc/pcr_linalg.cuh"
 #include "../../point_cloud_registration_b200/csrc/pcr_terms.cuh"
+#include "../../point_cloud_registration_b200/csrc/pcr_tile.cuh"
 
 using namespace pcr;
 
@@ -364,6 +365,166 @@ void hs_eig3(const double* c6, int64_t n, double* v) {
 void hs_icov(const double* cov, int64_t n, double* icov) {
     for (int64_t i = 0; i < n; ++i) icov_closed_form(cov + 9 * i, icov + 9 * i);
 }
+
+// ---- tile-stream search (pcr_tile.cuh): host replay of one warp row at a time -------------------
+// Same per-lane functions as the kernel; the warp glue of tile_search_row (leader election, cell box,
+// table pass, staging in pieces of `cap` points / `cscap` cell starts, settle test, halo doubling)
+// is restated with plain loops over 32 lane states.
+struct HostTile {
+    TileGrid v{};
+    std::vector<uint32_t> cs;
+    std::vector<float4> pts;
+    std::vector<uint32_t> perm;
+};
+
+void* hs_tile_build(const float* xyz, int64_t n, double c) {
+    HostTile* t = new HostTile();
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    double maxabs = 0;
+    for (int64_t i = 0; i < n; ++i)
+        for (int a = 0; a < 3; ++a) {
+            lo[a] = std::min(lo[a], xyz[3 * i + a]); hi[a] = std::max(hi[a], xyz[3 * i + a]);
+            maxabs = std::max(maxabs, (double)fabsf(xyz[3 * i + a]));
+        }
+    TileGrid& V = t->v;
+    V.c = (float)c; V.inv_c = (float)(1.0 / c); V.inv_c2 = V.inv_c * V.inv_c;
+    V.ox = lo[0] - 1.5f * V.c; V.oy = lo[1] - 1.5f * V.c; V.oz = lo[2] - 1.5f * V.c;
+    double d[3];
+    for (int a = 0; a < 3; ++a) d[a] = floor(((double)hi[a] - (double)(lo[a] - 1.5f * V.c)) / c) + 3.0;
+    V.nx = (int)d[0]; V.ny = (int)d[1]; V.nz = (int)d[2];
+    V.slack = 1e-3f + 1e-6f * (float)(2.0 * maxabs / c + (double)std::max(V.nx, std::max(V.ny, V.nz)));
+    V.n = (uint32_t)n;
+    const size_t ncells = (size_t)V.nx * V.ny * V.nz;
+    std::vector<uint32_t> key(n);
+    t->cs.assign(ncells + 1, 0u);
+    for (int64_t i = 0; i < n; ++i) {
+        const float gx = (xyz[3 * i] - V.ox) * V.inv_c, gy = (xyz[3 * i + 1] - V.oy) * V.inv_c, gz = (xyz[3 * i + 2] - V.oz) * V.inv_c;
+        const int cx = cell_of(gx, V.nx), cy = cell_of(gy, V.ny), cz = cell_of(gz, V.nz);
+        key[i] = (uint32_t)(((size_t)cz * V.ny + cy) * V.nx + cx);
+        t->cs[key[i] + 1]++;
+    }
+    for (size_t k = 0; k < ncells; ++k) t->cs[k + 1] += t->cs[k];
+    std::vector<uint32_t> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
+    t->pts.resize(n); t->perm.resize(n);
+    for (int64_t i = 0; i < n; ++i) {
+        const uint32_t j = order[i], pi = (uint32_t)i;
+        float w;
+        memcpy(&w, &pi, 4);
+        t->pts[i] = make_float4(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2], w);
+        t->perm[i] = j;
+    }
+    V.cs = t->cs.data(); V.pts = t->pts.data();
+    return t;
+}
+void hs_tile_free(void* t) { delete (HostTile*)t; }
+
+// q: (m,3) queries already posed, processed in rows of 32 in the given order.  idx: caller index of
+// the match or -1; dist: its distance; stats[0] = passes, [1] = staged batches, [2] = global-path rows,
+// [3] = staged points, [4] = rows that used ring order
+void hs_tile_nn(void* tp, const float* qs, int64_t m, double max_dist, int cap, int cscap, int core_e, double hint,
+                int64_t* idx, float* dist, int64_t* stats) {
+    HostTile* t = (HostTile*)tp;
+    const TileGrid& G = t->v;
+    const float md = (float)max_dist, max_d2 = md * md;
+    const float rmax = tile_rmax(G, max_d2);
+    std::vector<float4> spts(cap);
+    std::vector<uint32_t> scs(cscap);
+    for (int64_t row0 = 0; row0 < m; row0 += 32) {
+        TileQuery q[32]; TileBest b[32]; bool valid[32]; float rl[32];
+        uint32_t todo = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int64_t i = row0 + l;
+            valid[l] = false;
+            b[l].d2 = max_d2; b[l].pos = kTileNone; b[l].x = b[l].y = b[l].z = 0.f;
+            q[l] = TileQuery{};
+            if (i < m && qs[3 * i] == qs[3 * i])
+                valid[l] = tile_make_query(G, qs[3 * i], qs[3 * i + 1], qs[3 * i + 2], q[l]) && !tile_query_far_outside(G, q[l], max_d2);
+            rl[l] = fminf(fmaxf((float)hint, 0.03125f), rmax);
+            if (valid[l]) todo |= 1u << l;
+        }
+        while (todo) {
+            stats[0]++;
+            const int leader = __builtin_ffs((int)todo) - 1;
+            bool elig[32];
+            float rho = 0.f;
+            for (int l = 0; l < 32; ++l) {
+                elig[l] = ((todo >> l) & 1u) && abs(q[l].ix - q[leader].ix) <= core_e && abs(q[l].iy - q[leader].iy) <= core_e &&
+                          abs(q[l].iz - q[leader].iz) <= core_e;
+                if (elig[l]) rho = fmaxf(rho, rl[l]);
+            }
+            TileBox U{INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN};
+            for (int l = 0; l < 32; ++l) {
+                if (!elig[l]) continue;
+                U.x0 = std::min(U.x0, tile_cell_floor(q[l].gx - rho)); U.x1 = std::max(U.x1, tile_cell_floor(q[l].gx + rho));
+                U.y0 = std::min(U.y0, tile_cell_floor(q[l].gy - rho)); U.y1 = std::max(U.y1, tile_cell_floor(q[l].gy + rho));
+                U.z0 = std::min(U.z0, tile_cell_floor(q[l].gz - rho)); U.z1 = std::max(U.z1, tile_cell_floor(q[l].gz + rho));
+            }
+            TileBox R{std::max(U.x0, 0), std::min(U.x1, G.nx - 1), std::max(U.y0, 0), std::min(U.y1, G.ny - 1), std::max(U.z0, 0), std::min(U.z1, G.nz - 1)};
+            if (R.x0 <= R.x1 && R.y0 <= R.y1 && R.z0 <= R.z1) {
+                const int rnx = R.x1 - R.x0 + 1, rny = R.y1 - R.y0 + 1, rnz = R.z1 - R.z0 + 1, W = rnx + 1, nrows = rny * rnz;
+                const int RB = std::min(32, cscap / W);
+                int ra = 0;
+                while (ra < nrows) {
+                    uint32_t gs[32], len[32], incl[32]; size_t base[32]; bool rowv[32];
+                    uint32_t run = 0; int nfit = 0;
+                    for (int l = 0; l < 32; ++l) {
+                        const int r = ra + l;
+                        rowv[l] = l < RB && r < nrows;
+                        gs[l] = 0; len[l] = 0; base[l] = 0;
+                        if (rowv[l]) {
+                            const int jz = R.z0 + r / rny, jy = R.y0 + r % rny;
+                            base[l] = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
+                            gs[l] = G.cs[base[l]]; len[l] = G.cs[base[l] + rnx] - gs[l];
+                        }
+                        run += len[l]; incl[l] = run;
+                        if (rowv[l] && incl[l] <= (uint32_t)cap) nfit++;
+                    }
+                    if (nfit == 0) {
+                        stats[2]++;
+                        const int jz = R.z0 + ra / rny, jy = R.y0 + ra % rny;
+                        const size_t gb = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
+                        for (int l = 0; l < 32; ++l)
+                            if (elig[l]) tile_visit_row(G, q[l], b[l], jy, jz, R.x0, R.x1, G.cs + gb, G.pts, INT_MIN);
+                        ra += 1;
+                        continue;
+                    }
+                    const uint32_t total = incl[nfit - 1];
+                    if (total > 0) {
+                        stats[1]++; stats[3] += total;
+                        for (int l = 0; l < nfit; ++l) {
+                            const uint32_t excl = incl[l] - len[l];
+                            for (uint32_t k = 0; k < len[l]; ++k) spts[excl + k] = G.pts[gs[l] + k];
+                            for (int j = 0; j <= rnx; ++j) scs[l * W + j] = G.cs[base[l] + j] - gs[l] + excl;
+                        }
+                        const bool whole = ra == 0 && nfit == nrows;
+                        if (whole) stats[4]++;
+                        for (int l = 0; l < 32; ++l) {
+                            if (!elig[l]) continue;
+                            if (whole) tile_search_rings(G, q[l], b[l], R, ra, nfit, W, scs.data(), spts.data());
+                            else tile_search_linear(G, q[l], b[l], R, ra, nfit, W, scs.data(), spts.data());
+                        }
+                    }
+                    ra += nfit;
+                }
+            }
+            for (int l = 0; l < 32; ++l) {
+                if (!elig[l]) continue;
+                const bool settled = rho >= rmax || tile_settled(G, q[l], b[l], U);
+                if (settled) todo &= ~(1u << l);
+                else rl[l] = fminf(b[l].pos != kTileNone ? tile_radius_for(G, b[l]) : fmaxf(2.0f * rho, 1.0f), rmax);
+            }
+        }
+        for (int l = 0; l < 32; ++l) {
+            const int64_t i = row0 + l;
+            if (i >= m) break;
+            if (b[l].pos != kTileNone) { idx[i] = t->perm[b[l].pos]; dist[i] = sqrtf(b[l].d2); }
+            else { idx[i] = -1; dist[i] = INFINITY; }
+        }
+    }
+}
+
 uint64_t hs_box_mask(int x0, int x1, int y0, int y1, int z0, int z1) { return brick_box_mask(x0, x1, y0, y1, z0, z1); }
 
 }  // extern "C"
