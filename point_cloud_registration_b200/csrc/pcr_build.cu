@@ -1096,14 +1096,22 @@ __global__ void tile_count_occupied_kernel(const uint32_t* __restrict__ hist, un
     if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
+// sorted points as PAIR records (see TileGrid::pairs): record p = points 2p, 2p+1 as
+// (x0, x1, y0, y1), (z0, z1, w0, w1); an odd tail gets a sentinel that can never win
 __global__ void tile_gather_kernel(const float4* __restrict__ src, const uint32_t* __restrict__ vals, long long n,
-                                   float4* __restrict__ pts, uint32_t* __restrict__ perm) {
+                                   float* __restrict__ pairs, uint32_t* __restrict__ perm) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t j = vals[i];
-    const float4 p = src[j];
-    pts[i] = make_float4(p.x, p.y, p.z, __uint_as_float((uint32_t)i));
-    perm[i] = j;
+    const long long n_even = (n + 1) / 2 * 2;
+    if (i >= n_even) return;
+    float4 p = make_float4(3.0e38f, 3.0e38f, 3.0e38f, __uint_as_float(0xffffffffu));
+    if (i < n) {
+        const uint32_t j = vals[i];
+        const float4 t = src[j];
+        p = make_float4(t.x, t.y, t.z, __uint_as_float((uint32_t)i));
+        perm[i] = j;
+    }
+    float* rec = pairs + (i >> 1) * 8 + (i & 1);
+    rec[0] = p.x; rec[2] = p.y; rec[4] = p.z; rec[6] = p.w;
 }
 
 // payload in row-grid order: mode 0 = one float4 per source point (normals in source order);
@@ -1138,9 +1146,9 @@ static int build_tile_index(pcr_ctx* ctx, const float4* src, long long n, double
         V.nx = V.ny = V.nz = 1; V.n = 0;
         PCR_CUDA(out.cs.ensure(2 * 4));
         PCR_CUDA(cudaMemsetAsync(out.cs.p, 0, 8, ctx->stream));
-        PCR_CUDA(out.pts.ensure(16));
+        PCR_CUDA(out.pts.ensure(32));
         PCR_CUDA(out.perm.ensure(4));
-        V.cs = out.cs.as<uint32_t>(); V.pts = out.pts.as<float4>();
+        V.cs = out.cs.as<uint32_t>(); V.pairs = out.pts.as<float4>();
         out.view = V; out.built = true; out.n_cells_occupied = 0;
         return PCR_OK;
     }
@@ -1219,12 +1227,12 @@ static int build_tile_index(pcr_ctx* ctx, const float4* src, long long n, double
         ctx->launches += 4;
         int rc = exclusive_sum_u32(ctx, out.cs.as<uint32_t>(), out.cs.as<uint32_t>(), (long long)(ncells + 1));
         if (rc) return rc;
-        PCR_CUDA(out.pts.ensure((size_t)n * sizeof(float4)));
+        PCR_CUDA(out.pts.ensure((size_t)(n + 1) * sizeof(float4)));
         PCR_CUDA(out.perm.ensure((size_t)n * 4));
-        tile_gather_kernel<<<blocks_for(n, 256), 256, 0, ctx->stream>>>(src, v_out, n, out.pts.as<float4>(), out.perm.as<uint32_t>());
+        tile_gather_kernel<<<blocks_for(n + 1, 256), 256, 0, ctx->stream>>>(src, v_out, n, out.pts.as<float>(), out.perm.as<uint32_t>());
         PCR_LAUNCH_CHECK();
         V.cs = out.cs.as<uint32_t>();
-        V.pts = out.pts.as<float4>();
+        V.pairs = out.pts.as<float4>();
         out.view = V;
         out.built = true;
         PCR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1383,11 +1391,11 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_PATH")) ctx->use_tile = strcmp(e, "lists") != 0;
     if (const char* e = getenv("PCR_TILE_PPC")) ctx->tile_ppc_tgt = atof(e) > 0.25 ? atof(e) : 8.0;
     if (const char* e = getenv("PCR_TILE_PPC_VOX")) ctx->tile_ppc_vox = atof(e) > 0.25 ? atof(e) : 4.0;
-    if (const char* e = getenv("PCR_TILE_CAP")) ctx->tile_cap = atoi(e) >= 256 && atoi(e) <= 4096 ? atoi(e) / 4 * 4 : 256;
-    if (const char* e = getenv("PCR_TILE_CSCAP")) ctx->tile_cscap = atoi(e) >= 64 && atoi(e) <= 8192 ? atoi(e) : 512;
+    if (const char* e = getenv("PCR_TILE_CAP")) ctx->tile_cap = atoi(e) >= 256 && atoi(e) <= 4096 ? atoi(e) / 64 * 64 : 384;
     if (const char* e = getenv("PCR_TILE_CORE")) ctx->tile_core_e = atoi(e) >= 0 && atoi(e) <= 16 ? atoi(e) : 8;
-    if (const char* e = getenv("PCR_TILE_MINB")) ctx->tile_min_blocks = atoi(e) >= 2 && atoi(e) <= 4 ? atoi(e) : 0;
+    if (const char* e = getenv("PCR_TILE_MINB")) ctx->tile_min_blocks = atoi(e) >= 3 && atoi(e) <= 4 ? atoi(e) : 0;
     if (const char* e = getenv("PCR_TILE_R0")) ctx->tile_first_radius = atof(e) > 0.0 ? (float)atof(e) : 0.5f;
+    if (const char* e = getenv("PCR_TILE_G")) ctx->tile_groups = (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8) ? atoi(e) : 4;
     if (const char* e = getenv("PCR_TILE_KR")) ctx->tile_rows_per_unit = atoi(e) == 2 || atoi(e) == 4 ? atoi(e) : 0;
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }

@@ -67,7 +67,7 @@ struct Grid {
 // Row grid + row-major point copy the tile-stream kernel stages from (see pcr_tile.cuh).
 struct TileIndex {
     TileGrid view{};
-    DevBuf cs, pts, perm;     // cell starts, points (x, y, z, own position), position -> position in the source index
+    DevBuf cs, pts, perm;     // cell starts, points as pair records, position -> position in the source index
     DevBuf pay, pay2;         // per-point payload in the same order: normals (PlaneICP / VPlaneICP); NDT inverse covariances
     long long n_cells_occupied = 0;
     long long pay_epoch = -1;
@@ -121,11 +121,11 @@ struct pcr_ctx {
     int use_tile = 1;             // 1: tile-stream kernel, 0: round-1 list kernels (A/B, PCR_PATH=lists)
     double tile_ppc_tgt = 8.0;    // desired mean points per occupied cell of the row grids
     double tile_ppc_vox = 4.0;
-    int tile_cap = 256;           // points a warp can stage at once
-    int tile_cscap = 512;         // cell-start words a warp can stage at once
+    int tile_cap = 384;           // points a warp can stage at once
     int tile_core_e = 8;          // lanes farther than this many cells from the leader wait for their own pass
     int tile_min_blocks = 0;      // resident blocks per SM requested (0: default)
     int tile_rows_per_unit = 0;   // warp rows per unit of work (2 or 4; 0: chosen from the scan size)
+    int tile_groups = 4;          // independent groups a warp row is searched as (1, 2, 4, 8; see tile_search_row)
     int record_matches = 0;       // 1: the tile kernel also parks the matched positions (pcr_debug_matches)
     long long normals_epoch = 0;
     float tile_first_radius = 0.5f;   // halo radius (cells) a new scan starts with

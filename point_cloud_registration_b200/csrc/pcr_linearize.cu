@@ -663,10 +663,10 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
 }
 
 // ---- tile-stream path -------------------------------------------------------------------------
-template <int METHOD, int MINB, int KR>
+template <int METHOD, int MINB, int KR, int NG>
 static int launch_tile_kernel(pcr_ctx* ctx, const LinParams& P, const TileParams& TP, int& cached_blocks) {
     const size_t smem = (size_t)TP.warp_bytes * (kLinThreads / 32);
-    auto kernel = tile_linearize_kernel<METHOD, MINB, KR>;
+    auto kernel = tile_linearize_kernel<METHOD, MINB, KR, NG>;
     if (cached_blocks == 0) {
         PCR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
@@ -684,6 +684,12 @@ static int launch_tile_kernel(pcr_ctx* ctx, const LinParams& P, const TileParams
     return PCR_OK;
 }
 
+template <int METHOD, int KR, int NG>
+static int launch_tile_minb(pcr_ctx* ctx, const LinParams& P, const TileParams& TP, int& cached_blocks) {
+    if (ctx->tile_min_blocks == 4) return launch_tile_kernel<METHOD, 4, KR, NG>(ctx, P, TP, cached_blocks);
+    return launch_tile_kernel<METHOD, 3, KR, NG>(ctx, P, TP, cached_blocks);
+}
+
 template <int METHOD>
 static int launch_tile(pcr_ctx* ctx, const LinParams& P) {
     const bool vox = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
@@ -695,27 +701,28 @@ static int launch_tile(pcr_ctx* ctx, const LinParams& P) {
     TP.perm = t.perm.as<uint32_t>();
     TP.match_out = ctx->record_matches ? ctx->scan_prev.as<int>() : nullptr;
     TP.cap = ctx->tile_cap;
-    TP.cscap = ctx->tile_cscap;
     TP.rmax = tile_rmax(t.view, P.max_d2);
     TP.core_e = ctx->tile_core_e;
     constexpr int KRMAX = 4;                       // match slots reserved per warp: [KRMAX][32] float4
-    TP.warp_bytes = (int)(((size_t)TP.cap * 16 + (size_t)TP.cscap * 4 + 16 + (size_t)KRMAX * 32 * 16 + 127) / 128 * 128);
+    TP.warp_bytes = (int)(((size_t)TP.cap * 16 + 16 + (size_t)KRMAX * 32 * 16 + 127) / 128 * 128);
     int* cache = ctx->lin_blocks_per_sm[METHOD];
-    const int mb = ctx->tile_min_blocks > 0 ? ctx->tile_min_blocks : 3;
     // rows per unit of work: 4 when every warp still gets many units, 2 for small scans (less tail)
     const long long rows = P.n_pad / 32;
     const bool big = ctx->tile_rows_per_unit > 0 ? ctx->tile_rows_per_unit >= 4 : rows >= (long long)ctx->sm_count * 32 * 4 * 8;
+    const int ng = ctx->tile_groups;
     if (big) {
-        switch (mb) {
-            case 2: return launch_tile_kernel<METHOD, 2, 4>(ctx, P, TP, cache[9]);
-            case 3: return launch_tile_kernel<METHOD, 3, 4>(ctx, P, TP, cache[9]);
-            default: return launch_tile_kernel<METHOD, 4, 4>(ctx, P, TP, cache[9]);
+        switch (ng) {
+            case 1: return launch_tile_minb<METHOD, 4, 1>(ctx, P, TP, cache[8]);
+            case 2: return launch_tile_minb<METHOD, 4, 2>(ctx, P, TP, cache[8]);
+            case 8: return launch_tile_minb<METHOD, 4, 8>(ctx, P, TP, cache[8]);
+            default: return launch_tile_minb<METHOD, 4, 4>(ctx, P, TP, cache[8]);
         }
     }
-    switch (mb) {
-        case 2: return launch_tile_kernel<METHOD, 2, 2>(ctx, P, TP, cache[10]);
-        case 3: return launch_tile_kernel<METHOD, 3, 2>(ctx, P, TP, cache[10]);
-        default: return launch_tile_kernel<METHOD, 4, 2>(ctx, P, TP, cache[10]);
+    switch (ng) {
+        case 1: return launch_tile_minb<METHOD, 2, 1>(ctx, P, TP, cache[9]);
+        case 2: return launch_tile_minb<METHOD, 2, 2>(ctx, P, TP, cache[9]);
+        case 8: return launch_tile_minb<METHOD, 2, 8>(ctx, P, TP, cache[9]);
+        default: return launch_tile_minb<METHOD, 2, 4>(ctx, P, TP, cache[9]);
     }
 }
 
@@ -945,6 +952,11 @@ int pcr_loop_begin(pcr_ctx* ctx, const double T0[16]) {
     ctx->h_out[49] = 0.0;
     loop_init_kernel<<<1, 32, 0, ctx->stream>>>(ctx->state.as<LoopState>(), t0);
     PCR_LAUNCH_CHECK();
+    if (ctx->use_tile && ctx->scan_set && ctx->n_scan_pad > 0) {
+        // a new trajectory starts from a new pose: the halo radii remembered from the last one are void
+        fill_float_kernel<<<(unsigned)((ctx->n_scan_pad / 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_hint.as<float>(), ctx->n_scan_pad / 32, ctx->tile_first_radius);
+        PCR_LAUNCH_CHECK();
+    }
     return PCR_OK;
 }
 

@@ -8,8 +8,11 @@
 //   * any run of cells [xa..xb] of one (y,z) row is ONE contiguous range of the point array,
 //     cs[row*nx + xa] .. cs[row*nx + xb + 1]: a box of cells is rny*rnz contiguous byte ranges,
 //     which is exactly what a 1-D bulk copy (cp.async.bulk, TMA engine) moves into shared memory;
-//   * the ball of the current best distance meets a row in one x-interval, so the per-lane search
-//     is "for each row near the query: one range loop" -- no per-cell walk.
+//   * once a box is staged, EVERY lane of the warp evaluates EVERY staged candidate: all lanes read
+//     the same shared-memory addresses (broadcast), nobody diverges, no per-lane cell walk exists
+//     (measured: a pruned per-lane walk of the same box ran at 9 of 32 active lanes and needed
+//     three times the instructions, profiles/r2_notes.md).  Candidates are stored as pair records
+//     so that two distances cost six packed f32x2 instructions.
 //
 // A warp takes 32 consecutive scan points (the scan is uploaded in cell order, so they sit in a
 // handful of neighbouring cells), stages the cells that meet the box [min - rho, max + rho] around
@@ -36,7 +39,9 @@ struct TileGrid {
     float slack;             // conservative inflation (grid units) covering float32 binning error
     int nx, ny, nz;          // cells per axis
     const uint32_t* cs;      // [nx*ny*nz + 1] first point of every cell, x fastest, then y, then z
-    const float4* pts;       // [n] (x, y, z, own position as uint32 bits), sorted by cell number
+    const float4* pairs;     // [2 * ceil(n / 2)] points sorted by cell number, stored as PAIR records of 32 bytes:
+                             //   pairs[2p] = (x0, x1, y0, y1), pairs[2p+1] = (z0, z1, w0, w1), w = own position (uint32 bits);
+                             //   an odd tail is filled with a sentinel that is infinitely far from every query
     uint32_t n;
 };
 
@@ -55,6 +60,8 @@ struct TileBest {
 };
 
 constexpr uint32_t kTileNone = 0xffffffffu;
+// host replay only (tests/hostsim): work counters of the per-lane search (never touched by device code)
+inline long long g_tile_evals = 0;
 constexpr float kTileCoordLimit = 1048576.0f;   // 2^20 cells
 
 // floor to a cell number, safe for any float (huge halo radii of an unbounded max_dist included)
@@ -84,106 +91,69 @@ PCR_HD bool tile_query_far_outside(const TileGrid& G, const TileQuery& q, float 
     return e * e >= max_d2 * G.inv_c2 * 1.00001f;
 }
 
-// candidates [lo, hi) of one range
-PCR_HD void tile_eval_range(const float4* pts, uint32_t lo, uint32_t hi, const TileQuery& q, TileBest& b) {
-    for (uint32_t s = lo; s < hi; ++s) {
-        const float4 t = pts[s];
-        const float d = dist2_rn(t.x - q.qx, t.y - q.qy, t.z - q.qz);
-        if (d < b.d2) {
-            b.d2 = d; b.x = t.x; b.y = t.y; b.z = t.z;
-#if defined(__CUDA_ARCH__)
-            b.pos = __float_as_uint(t.w);
+// Squared distances of the two candidates of one pair record (see TileGrid::pairs) to one query,
+// with the rounding sequence of dist2_rn (packed f32x2 arithmetic on sm_100: six instructions).
+PCR_HD void tile_pair_d2(const float4& A, float bz0, float bz1, const TileQuery& q, float& d0, float& d1) {
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
+    const float2 ex = __fadd2_rn(make_float2(A.x, A.y), make_float2(-q.qx, -q.qx));
+    const float2 ey = __fadd2_rn(make_float2(A.z, A.w), make_float2(-q.qy, -q.qy));
+    const float2 ez = __fadd2_rn(make_float2(bz0, bz1), make_float2(-q.qz, -q.qz));
+    const float2 r = __ffma2_rn(ez, ez, __ffma2_rn(ey, ey, __fmul2_rn(ex, ex)));
+    d0 = r.x; d1 = r.y;
 #else
-            memcpy(&b.pos, &t.w, 4);
+    d0 = dist2_rn(A.x - q.qx, A.z - q.qy, bz0 - q.qz);
+    d1 = dist2_rn(A.y - q.qx, A.w - q.qy, bz1 - q.qz);
 #endif
+}
+
+// Every lane evaluates EVERY staged candidate: `np` pair records at `pairs` (shared or global memory,
+// the same addresses for all lanes of the warp: broadcast loads, no divergence), four candidates per
+// trip; only the minimum of a trip is compared with the best, and only the trip that improved it is
+// remembered (three instructions) -- tile_take finds the winner inside that trip afterwards.
+// Returns the first pair of the winning trip or kTileNone; `best` is updated.
+PCR_HD uint32_t tile_scan_pairs(const float4* pairs, uint32_t np, const TileQuery& q, float& best) {
+    uint32_t trip = kTileNone;
+    uint32_t p = 0;
+    for (; p + 2 <= np; p += 2) {
+        const float4 A0 = pairs[2 * p], B0 = pairs[2 * p + 1], A1 = pairs[2 * p + 2], B1 = pairs[2 * p + 3];
+        float d0, d1, d2, d3;
+        tile_pair_d2(A0, B0.x, B0.y, q, d0, d1);
+        tile_pair_d2(A1, B1.x, B1.y, q, d2, d3);
+        const float dm = fminf(fminf(d0, d1), fminf(d2, d3));
+        if (dm < best) { best = dm; trip = p; }
+    }
+    if (p < np) {
+        const float4 A0 = pairs[2 * p], B0 = pairs[2 * p + 1];
+        float d0, d1;
+        tile_pair_d2(A0, B0.x, B0.y, q, d0, d1);
+        const float dm = fminf(d0, d1);
+        if (dm < best) { best = dm; trip = p; }
+    }
+#if !defined(__CUDA_ARCH__)
+    g_tile_evals += 2 * (long long)np;
+#endif
+    return trip;
+}
+
+// the candidate of the trip starting at pair `trip` whose distance is `best` -> b (the distances are
+// recomputed with the same roundings, so the comparison is exact; first of equals wins)
+PCR_HD void tile_take(const float4* pairs, uint32_t trip, uint32_t np, const TileQuery& q, float best, TileBest& b) {
+    const uint32_t pe = trip + 2 <= np ? trip + 2 : np;
+    for (uint32_t p = trip; p < pe; ++p) {
+        const float4 A = pairs[2 * p], B = pairs[2 * p + 1];
+        float d0, d1;
+        tile_pair_d2(A, B.x, B.y, q, d0, d1);
+        if (d0 == best || d1 == best) {
+            const bool hi = d0 != best;
+            b.d2 = best; b.x = hi ? A.y : A.x; b.y = hi ? A.w : A.z; b.z = hi ? B.y : B.x;
+            const float w = hi ? B.w : B.z;
+#if defined(__CUDA_ARCH__)
+            b.pos = __float_as_uint(w);
+#else
+            memcpy(&b.pos, &w, 4);
+#endif
+            return;
         }
-    }
-}
-
-// One (jy, jz) row whose cells X0..X1 are addressable: csrow[j] = index in `pts` of the first point
-// of cell X0 + j (j = 0 .. X1 - X0 + 1).  Evaluates the cells the ball of the current best meets;
-// skip_ix = a cell of this row that has been evaluated already (INT_MIN: none).
-PCR_HD void tile_visit_row(const TileGrid& G, const TileQuery& q, TileBest& b, int jy, int jz, int X0, int X1,
-                           const uint32_t* csrow, const float4* pts, int skip_ix) {
-    const float dy = fmaxf(fmaxf((float)jy - q.gy, q.gy - (float)(jy + 1)) - G.slack, 0.0f);
-    const float dz = fmaxf(fmaxf((float)jz - q.gz, q.gz - (float)(jz + 1)) - G.slack, 0.0f);
-    const float r2 = b.d2 * G.inv_c2 * 1.00001f;                 // pruning radius^2 in grid units, rounded up
-    const float rem = r2 - (dy * dy + dz * dz);
-    if (!(rem > 0.0f)) return;                                   // the row's (y,z) rectangle is beyond the best
-    const float rx = sqrtf(rem) * 1.000001f + G.slack;
-    int xa = tile_cell_floor(q.gx - rx), xb = tile_cell_floor(q.gx + rx);
-    xa = xa > X0 ? xa : X0;
-    xb = xb < X1 ? xb : X1;
-    if (xa > xb) return;
-    if (skip_ix >= xa && skip_ix <= xb) {
-        tile_eval_range(pts, csrow[xa - X0], csrow[skip_ix - X0], q, b);
-        tile_eval_range(pts, csrow[skip_ix + 1 - X0], csrow[xb + 1 - X0], q, b);
-    } else {
-        tile_eval_range(pts, csrow[xa - X0], csrow[xb + 1 - X0], q, b);
-    }
-}
-
-// e-th row offset (dy, dz) of the Chebyshev ring k >= 1 around the own row (8k rows)
-PCR_HD void tile_ring_offset(int k, int e, int& dy, int& dz) {
-    const int s = 2 * k + 1;
-    if (e < s) { dz = -k; dy = e - k; }
-    else if (e < 2 * s) { dz = k; dy = e - s - k; }
-    else if (e < 3 * s - 2) { dy = -k; dz = e - 2 * s - k + 1; }
-    else { dy = k; dz = e - (3 * s - 2) - k + 1; }
-}
-
-// The rows of box R with row numbers [ra, ra + nfit) are resident (row number r = (jy - R.y0) +
-// rny * (jz - R.z0); scs[(r - ra) * W + j] = index in spts of the first point of cell R.x0 + j).
-// RING ORDER: own cell, own row, then the rings of rows around it, nearest first, stopping as soon
-// as a whole ring is beyond the best -- for a box that is resident in one piece.
-PCR_HD void tile_search_rings(const TileGrid& G, const TileQuery& q, TileBest& b, const TileBox& R, int ra, int nfit, int W,
-                              const uint32_t* scs, const float4* spts) {
-    const int rny = R.y1 - R.y0 + 1;
-    const bool own_row_in = q.iy >= R.y0 && q.iy <= R.y1 && q.iz >= R.z0 && q.iz <= R.z1;
-    if (own_row_in) {
-        const int lr = (q.iy - R.y0) + rny * (q.iz - R.z0) - ra;
-        if (lr >= 0 && lr < nfit) {
-            const uint32_t* csrow = scs + lr * W;
-            int skip = INT_MIN;
-            if (q.ix >= R.x0 && q.ix <= R.x1) {
-                tile_eval_range(spts, csrow[q.ix - R.x0], csrow[q.ix + 1 - R.x0], q, b);
-                skip = q.ix;
-            }
-            tile_visit_row(G, q, b, q.iy, q.iz, R.x0, R.x1, csrow, spts, skip);
-        }
-    }
-    // distance (grid units) from the query to the nearest (y,z) face of its own row: a lower
-    // bound of ring k's distance is (k - 1) + that
-    const float fy = q.gy - (float)q.iy, fz = q.gz - (float)q.iz;
-    const float myz = fminf(fminf(fy, 1.0f - fy), fminf(fz, 1.0f - fz));
-    int kmax = q.iy - R.y0;
-    kmax = (R.y1 - q.iy) > kmax ? (R.y1 - q.iy) : kmax;
-    kmax = (q.iz - R.z0) > kmax ? (q.iz - R.z0) : kmax;
-    kmax = (R.z1 - q.iz) > kmax ? (R.z1 - q.iz) : kmax;
-    for (int k = 1; k <= kmax; ++k) {
-        const float lb = (float)(k - 1) + myz - G.slack;
-        if (lb > 0.0f && lb * lb >= b.d2 * G.inv_c2 * 1.00001f) break;
-        for (int e = 0; e < 8 * k; ++e) {
-            int dy, dz;
-            tile_ring_offset(k, e, dy, dz);
-            const int jy = q.iy + dy, jz = q.iz + dz;
-            if (jy < R.y0 || jy > R.y1 || jz < R.z0 || jz > R.z1) continue;
-            const int lr = (jy - R.y0) + rny * (jz - R.z0) - ra;
-            if (lr < 0 || lr >= nfit) continue;
-            tile_visit_row(G, q, b, jy, jz, R.x0, R.x1, scs + lr * W, spts, INT_MIN);
-        }
-    }
-}
-
-// MEMORY ORDER: every resident row once, pruned by the best -- for one batch of a box that is
-// staged in several pieces (large halos).
-PCR_HD void tile_search_linear(const TileGrid& G, const TileQuery& q, TileBest& b, const TileBox& R, int ra, int nfit, int W,
-                               const uint32_t* scs, const float4* spts) {
-    const int rny = R.y1 - R.y0 + 1;
-    for (int lr = 0; lr < nfit; ++lr) {
-        const int r = ra + lr;
-        const int jz = R.z0 + r / rny, jy = R.y0 + r % rny;
-        tile_visit_row(G, q, b, jy, jz, R.x0, R.x1, scs + lr * W, spts, INT_MIN);
     }
 }
 
@@ -199,23 +169,27 @@ PCR_HD float tile_guarantee(const TileGrid& G, const TileQuery& q, const TileBox
     return g - G.slack;
 }
 
-// the best is final: nothing outside the staged box can be closer (also true for "no match": the
-// pruning radius is then max_dist itself), or the box held the whole grid
+PCR_HD bool tile_box_holds_grid(const TileGrid& G, const TileBox& U) {
+    return U.x0 <= 0 && U.y0 <= 0 && U.z0 <= 0 && U.x1 >= G.nx - 1 && U.y1 >= G.ny - 1 && U.z1 >= G.nz - 1;
+}
+
+// the best is final: nothing outside the staged box can be closer (also true for "no match": b.d2
+// is then max_dist^2 itself), or the box held the whole grid
 PCR_HD bool tile_settled(const TileGrid& G, const TileQuery& q, const TileBest& b, const TileBox& U) {
-    if (U.x0 <= 0 && U.y0 <= 0 && U.z0 <= 0 && U.x1 >= G.nx - 1 && U.y1 >= G.ny - 1 && U.z1 >= G.nz - 1) return true;
+    if (tile_box_holds_grid(G, U)) return true;
     const float g = tile_guarantee(G, q, U);
     return g > 0.0f && b.d2 * G.inv_c2 * 1.00001f <= g * g;
+}
+
+// Halo radius that settles a lane for certain in the NEXT pass: the ball of its current candidate.
+PCR_HD float tile_radius_for(const TileGrid& G, const TileBest& b) {
+    return sqrtf(b.d2) * G.inv_c * 1.00001f + 2.0f * G.slack;
 }
 
 // Halo radius (grid units) at which every joined lane is settled whatever it found: a lane is at
 // least radius - slack away from every face of the box staged around the joined lanes.
 PCR_HD float tile_rmax(const TileGrid& G, float max_d2) {
     return sqrtf(max_d2) * G.inv_c * 1.00001f + 2.0f * G.slack + 1.0e-3f;
-}
-
-// Halo radius that settles a lane for certain in the NEXT pass: the ball of its current candidate.
-PCR_HD float tile_radius_for(const TileGrid& G, const TileBest& b) {
-    return sqrtf(b.d2) * G.inv_c * 1.00001f + 2.0f * G.slack;
 }
 
 }  // namespace pcr

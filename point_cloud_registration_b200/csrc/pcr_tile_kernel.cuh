@@ -3,12 +3,13 @@
 // finish_iteration, load_pose).
 //
 // One warp = one row of 32 consecutive scan points (cell-ordered on upload):
-//   coalesced SoA loads -> float32 SE(3) transform -> cell of every lane -> cell box of the row
-//   (+ halo) -> per (y,z) row of that box ONE bulk copy global -> shared (cp.async.bulk, completion
-//   on an mbarrier: SASS UBLKCP + SYNCS) of its contiguous point range, cell starts alongside ->
-//   every lane searches the staged box from shared memory (pcr_tile.cuh) -> settle test -> halo
-//   doubled for the lanes still open -> matched record gathered once -> residual + Jacobian terms
-//   in registers -> float64 reduction -> last block assembles the record and does the GN step.
+//   coalesced SoA loads -> float32 SE(3) transform -> cells meeting the box [min - rho, max + rho]
+//   of the row -> per (y,z) row of that box ONE bulk copy global -> shared (cp.async.bulk,
+//   completion on an mbarrier: SASS UBLKCP + SYNCS) of its contiguous range of pair records ->
+//   every lane evaluates every staged candidate (broadcast shared-memory loads, packed f32x2
+//   distances, no divergence; pcr_tile.cuh) -> settle test -> larger box for the lanes still open
+//   -> matched record gathered once -> residual + Jacobian terms in registers -> float64 reduction
+//   -> last block assembles the record and does the GN step.
 // No per-point list structure, no parked positions, no second kernel: compulsory traffic is the
 // scan, the staged target ranges (L2-resident between neighbouring rows) and one payload gather.
 #pragma once
@@ -24,7 +25,6 @@ struct TileParams {
     const uint32_t* perm;     // position -> position in the source index (only for match_out)
     int* match_out;           // optional [n_pad]: matched source position per scan slot (-1 none)
     int cap;                  // points per warp stage buffer
-    int cscap;                // cell-start words per warp stage buffer
     float rmax;               // halo radius at which every lane is settled by construction
     int core_e;               // lanes farther than this many cells from the leader wait for their own pass
     int warp_bytes;           // shared-memory stride between the stage buffers of two warps
@@ -68,16 +68,47 @@ __device__ __forceinline__ void tile_flush(float* acc, double& acc64, float* scr
     __syncwarp();
 }
 
+// min / max over the L consecutive lanes of a group (every lane of the warp takes part: xor butterflies
+// inside the groups; the whole warp at once is one redux instruction)
+template <int L>
+__device__ __forceinline__ int group_min(int v) {
+    if (L == 32) return __reduce_min_sync(0xffffffffu, v);
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+template <int L>
+__device__ __forceinline__ int group_max(int v) {
+    if (L == 32) return __reduce_max_sync(0xffffffffu, v);
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
 // search half of one warp row: the matched point (x, y, z, position bits; position 0xffffffff = no
-// correspondence) of every lane is parked in shared memory for the accumulate half
+// correspondence) of every lane is parked in shared memory for the accumulate half.
+//
+// The warp works as NG independent GROUPS of L = 32 / NG consecutive lanes: every group stages its
+// OWN box (the cells around its L scan points) into its own slice of the stage buffer, and its lanes
+// scan only that slice.  Scanning costs (lanes x staged candidates); L consecutive scan points span
+// ~L / ppc cells, so smaller groups stage far fewer candidates per lane, while all groups still run
+// the same instructions (broadcast loads inside a group, NG distinct addresses per request).
+template <int NG>
 __device__ __forceinline__ void tile_search_row(const LinParams& P, const TileParams& TP, const Pose32* spose, long long row, int lane,
-                                                float4* spts, uint32_t* scs, uint64_t* bar, uint32_t& phase, float4* smatch) {
+                                                float4* spts, uint64_t* bar, uint32_t& phase, float4* smatch) {
     constexpr unsigned FULL = 0xffffffffu;
+    constexpr int L = 32 / NG;
     const TileGrid& G = TP.G;
+    const int gl = lane & (L - 1), gbase = lane & ~(L - 1);     // lane within its group, first lane of the group
+    const unsigned gmask = (NG == 1 ? FULL : ((1u << L) - 1u)) << gbase;
+    const uint32_t capp = ((uint32_t)TP.cap >> 1) / NG;          // this group's slice of the stage buffer, in pair records
+    float4* gpts = spts + 2 * (size_t)capp * (lane / L);
     const long long i = row * 32 + lane;
     const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+    const float nanf_ = __int_as_float(0x7fc00000);
     TileQuery q;
-    q.qx = q.qy = q.qz = q.gx = q.gy = q.gz = 0.f; q.ix = q.iy = q.iz = 0;
+    q.qx = q.qy = q.qz = nanf_;                                  // a lane without a query compares false against every candidate
+    q.gx = q.gy = q.gz = 0.f; q.ix = q.iy = q.iz = 0;
     TileBest b;
     b.d2 = P.max_d2; b.pos = kTileNone; b.x = b.y = b.z = 0.f;
     bool valid = false;
@@ -90,83 +121,77 @@ __device__ __forceinline__ void tile_search_row(const LinParams& P, const TilePa
     float rl = fminf(fmaxf(hint_in, kTileMinRadius), TP.rmax);   // this lane's halo radius (grid units)
     unsigned todo = __ballot_sync(FULL, valid);
     while (todo) {
-        // ---- one pass: leader = first open lane; everybody near it joins, the halo is the largest any of them asks for ----
-        const int leader = __ffs(todo) - 1;
+        // ---- one pass (per group): leader = first open lane; everybody near it joins, the halo is the largest any of them asks for ----
+        const unsigned gtodo = todo & gmask;
+        const int leader = gtodo ? __ffs(gtodo) - 1 : lane;
         const int lx = __shfl_sync(FULL, q.ix, leader), ly = __shfl_sync(FULL, q.iy, leader), lz = __shfl_sync(FULL, q.iz, leader);
         const bool elig = ((todo >> lane) & 1u) && abs(q.ix - lx) <= TP.core_e && abs(q.iy - ly) <= TP.core_e && abs(q.iz - lz) <= TP.core_e;
-        const float rho = __int_as_float(__reduce_max_sync(FULL, elig ? __float_as_int(rl) : 0));   // radii are positive: bit order = value order
+        const float rho = __int_as_float(group_max<L>(elig ? __float_as_int(rl) : 0));   // radii are positive: bit order = value order
         TileBox U;                                               // cells meeting [min - rho, max + rho] of the joined lanes (not clipped)
-        U.x0 = __reduce_min_sync(FULL, elig ? tile_cell_floor(q.gx - rho) : INT_MAX); U.x1 = __reduce_max_sync(FULL, elig ? tile_cell_floor(q.gx + rho) : INT_MIN);
-        U.y0 = __reduce_min_sync(FULL, elig ? tile_cell_floor(q.gy - rho) : INT_MAX); U.y1 = __reduce_max_sync(FULL, elig ? tile_cell_floor(q.gy + rho) : INT_MIN);
-        U.z0 = __reduce_min_sync(FULL, elig ? tile_cell_floor(q.gz - rho) : INT_MAX); U.z1 = __reduce_max_sync(FULL, elig ? tile_cell_floor(q.gz + rho) : INT_MIN);
+        U.x0 = group_min<L>(elig ? tile_cell_floor(q.gx - rho) : INT_MAX); U.x1 = group_max<L>(elig ? tile_cell_floor(q.gx + rho) : INT_MIN);
+        U.y0 = group_min<L>(elig ? tile_cell_floor(q.gy - rho) : INT_MAX); U.y1 = group_max<L>(elig ? tile_cell_floor(q.gy + rho) : INT_MIN);
+        U.z0 = group_min<L>(elig ? tile_cell_floor(q.gz - rho) : INT_MAX); U.z1 = group_max<L>(elig ? tile_cell_floor(q.gz + rho) : INT_MIN);
         TileBox R;                                               // the part of it inside the grid
         R.x0 = max(U.x0, 0); R.x1 = min(U.x1, G.nx - 1);
         R.y0 = max(U.y0, 0); R.y1 = min(U.y1, G.ny - 1);
         R.z0 = max(U.z0, 0); R.z1 = min(U.z1, G.nz - 1);
-        if (R.x0 <= R.x1 && R.y0 <= R.y1 && R.z0 <= R.z1) {
-            const int rnx = R.x1 - R.x0 + 1, rny = R.y1 - R.y0 + 1, rnz = R.z1 - R.z0 + 1;
-            const int W = rnx + 1;
-            const int nrows = rny * rnz;
-            const int RB = min(32, TP.cscap / W);                // rows whose cell starts fit the stage buffer
-            int ra = 0;
-            while (ra < nrows) {
-                // ---- table pass: lane l looks up the point range of row ra + l ----
-                const int r = ra + lane;
-                const bool rowv = lane < RB && r < nrows;
-                uint32_t gs = 0u, ge = 0u;
-                size_t base = 0;
-                if (rowv) {
-                    const int jz = R.z0 + r / rny, jy = R.y0 + r % rny;
-                    base = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
-                    gs = __ldg(G.cs + base);
-                    ge = __ldg(G.cs + base + rnx);
-                }
-                const uint32_t len = ge - gs;
-                uint32_t incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const uint32_t t = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += t;
-                }
-                const int nfit = __popc(__ballot_sync(FULL, rowv && incl <= (uint32_t)TP.cap));   // a prefix: incl is monotone
-                if (nfit == 0) {
-                    // row ra alone exceeds the stage buffer (or no cell-start room at all): search it in global memory
-                    const int jz = R.z0 + ra / rny, jy = R.y0 + ra % rny;
-                    const size_t gb = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
-                    if (elig) tile_visit_row(G, q, b, jy, jz, R.x0, R.x1, G.cs + gb, G.pts, INT_MIN);
-                    ra += 1;
-                    continue;
-                }
-                const uint32_t total = __shfl_sync(FULL, incl, nfit - 1);
-                if (total > 0u) {
-                    // ---- stage: one bulk copy per non-empty row, cell starts rebased to the stage buffer ----
-                    const uint32_t excl = incl - len;
-                    if (lane == 0) mbar_expect_tx(bar, total * 16u);
-                    __syncwarp();
-                    if (lane < nfit) {
-                        if (len) bulk_g2s(spts + excl, G.pts + gs, len * 16u, bar);
-                        const uint32_t bias = excl - gs;
-                        uint32_t* dst = scs + lane * W;
-                        for (int j = 0; j <= rnx; ++j) dst[j] = __ldg(G.cs + base + j) + bias;
-                    }
-                    __syncwarp();
-                    mbar_wait(bar, phase);
-                    phase ^= 1u;
-                    if (elig) {
-                        if (ra == 0 && nfit == nrows) tile_search_rings(G, q, b, R, ra, nfit, W, scs, spts);
-                        else tile_search_linear(G, q, b, R, ra, nfit, W, scs, spts);
-                    }
-                    __syncwarp();                                // everybody is done reading before the next stage overwrites
-                }
-                ra += nfit;
+        const bool box = gtodo != 0u && R.x0 <= R.x1 && R.y0 <= R.y1 && R.z0 <= R.z1;
+        const int rnx = R.x1 - R.x0 + 1, rny = box ? R.y1 - R.y0 + 1 : 1, rnz = R.z1 - R.z0 + 1;
+        const int nrows = box ? rny * rnz : 0;                   // (y,z) rows of this group's box
+        int ra = 0;
+        while (__any_sync(FULL, ra < nrows)) {
+            // ---- table pass: lane l of the group looks up the pair range of row ra + l of the group's box ----
+            const int r = ra + gl;
+            const bool rowv = r < nrows;
+            uint32_t ps = 0u, lenp = 0u;
+            if (rowv) {
+                const int jz = R.z0 + r / rny, jy = R.y0 + r % rny;
+                const size_t base = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
+                const uint32_t gs = __ldg(G.cs + base), ge = __ldg(G.cs + base + rnx);
+                if (ge > gs) { ps = gs >> 1; lenp = ((ge + 1u) >> 1) - ps; }   // whole pair records: a neighbour point at either end is harmless
             }
+            uint32_t incl = lenp;
+#pragma unroll
+            for (int o = 1; o < L; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(FULL, incl, o, L);
+                if (gl >= o) incl += t;
+            }
+            const int nfit = __popc(__ballot_sync(FULL, rowv && incl <= capp) & gmask);   // a prefix of the group: incl is monotone
+            // mode of this group for this piece: 0 nothing left, 1 staged, 2 its next row alone exceeds the slice: scanned in global memory
+            const int mode = ra >= nrows ? 0 : (nfit > 0 ? 1 : 2);
+            // (every warp-wide shuffle is executed by ALL lanes, whatever their group's mode: a full-mask shuffle
+            //  inside a per-group condition would wait for lanes that never arrive)
+            const uint32_t total_any = __shfl_sync(FULL, incl, gbase + (nfit > 0 ? nfit - 1 : 0));
+            const uint32_t total = mode == 1 ? total_any : 0u;
+            const uint32_t all = __reduce_add_sync(FULL, gl == 0 ? total : 0u);
+            if (all > 0u) {
+                // ---- stage: one bulk copy per non-empty row, then every lane scans EVERY candidate its group staged ----
+                if (lane == 0) mbar_expect_tx(bar, all * 32u);
+                __syncwarp();
+                if (mode == 1 && gl < nfit && lenp) bulk_g2s(gpts + 2 * (incl - lenp), G.pairs + 2 * (size_t)ps, lenp * 32u, bar);
+                mbar_wait(bar, phase);
+                phase ^= 1u;
+                float best = b.d2;
+                const uint32_t trip = tile_scan_pairs(gpts, total, q, best);
+                if (trip != kTileNone) tile_take(gpts, trip, total, q, best, b);
+                __syncwarp();                                    // everybody is done reading before the next piece overwrites
+            }
+            if (__any_sync(FULL, mode == 2)) {
+                const uint32_t ps0 = __shfl_sync(FULL, ps, gbase), np_any = __shfl_sync(FULL, lenp, gbase);
+                const uint32_t np0 = mode == 2 ? np_any : 0u;
+                const float4* gp = G.pairs + 2 * (size_t)ps0;
+                float best = b.d2;
+                const uint32_t trip = tile_scan_pairs(gp, np0, q, best);
+                if (trip != kTileNone) tile_take(gp, trip, np0, q, best, b);
+            }
+            ra += mode == 1 ? nfit : (mode == 2 ? 1 : 0);
         }
         // ---- settle: final iff nothing outside the staged box can be closer; else ask for the ball of the
         //      candidate (settles for certain next time) or, with no candidate yet, for twice the radius ----
         bool settled = false;
         if (elig) {
             settled = rho >= TP.rmax || tile_settled(G, q, b, U);
-            if (!settled) rl = fminf(b.pos != kTileNone ? tile_radius_for(G, b) : fmaxf(2.0f * rho, 1.0f), TP.rmax);
+            if (!settled) rl = fminf(b.pos != kTileNone ? tile_radius_for(G, b) : 2.0f * rho, TP.rmax);
         }
         todo &= ~__ballot_sync(FULL, settled);
     }
@@ -204,7 +229,7 @@ __device__ __forceinline__ void tile_accumulate_row(const LinParams& P, const Ti
 
 // KR consecutive warp rows form one unit of work: their searches run first (the 29 accumulators are
 // dead meanwhile -- the search keeps its registers), then their terms are accumulated and flushed
-template <int METHOD, int MINB, int KR>
+template <int METHOD, int MINB, int KR, int NG>
 __global__ void __launch_bounds__(kLinThreads, MINB) tile_linearize_kernel(const LinParams P, const TileParams TP) {
     extern __shared__ __align__(128) unsigned char tile_smem[];
     __shared__ BlockShared sh;
@@ -220,9 +245,8 @@ __global__ void __launch_bounds__(kLinThreads, MINB) tile_linearize_kernel(const
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wbase = tile_smem + (size_t)warp * TP.warp_bytes;
     float4* spts = reinterpret_cast<float4*>(wbase);
-    uint32_t* scs = reinterpret_cast<uint32_t*>(wbase + (size_t)TP.cap * 16);
-    uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + (size_t)TP.cap * 16 + (size_t)TP.cscap * 4);
-    float4* smatch = reinterpret_cast<float4*>(wbase + (size_t)TP.cap * 16 + (size_t)TP.cscap * 4 + 16);   // [KR][32]
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + (size_t)TP.cap * 16);
+    float4* smatch = reinterpret_cast<float4*>(wbase + (size_t)TP.cap * 16 + 16);   // [KR][32]
     if (lane == 0) {
         mbar_init(bar, 1u);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -237,7 +261,7 @@ __global__ void __launch_bounds__(kLinThreads, MINB) tile_linearize_kernel(const
         const long long row0 = grp * KR;
 #pragma unroll 1
         for (int u = 0; u < KR; ++u)
-            if (row0 + u < rows) tile_search_row(P, TP, &spose, row0 + u, lane, spts, scs, bar, phase, smatch + u * 32);
+            if (row0 + u < rows) tile_search_row<NG>(P, TP, &spose, row0 + u, lane, spts, bar, phase, smatch + u * 32);
         __syncwarp();
         float acc[NACC];
 #pragma unroll

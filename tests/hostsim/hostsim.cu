@@ -367,13 +367,13 @@ void hs_icov(const double* cov, int64_t n, double* icov) {
 }
 
 // ---- tile-stream search (pcr_tile.cuh): host replay of one warp row at a time -------------------
-// Same per-lane functions as the kernel; the warp glue of tile_search_row (leader election, cell box,
-// table pass, staging in pieces of `cap` points / `cscap` cell starts, settle test, halo doubling)
-// is restated with plain loops over 32 lane states.
+// Same per-lane functions as the kernel; the warp glue of tile_search_row (leader election, staged
+// cell box, table pass, staging in pieces of `cap` points, settle test, next radius) is restated with
+// plain loops over 32 lane states.
 struct HostTile {
     TileGrid v{};
     std::vector<uint32_t> cs;
-    std::vector<float4> pts;
+    std::vector<float4> pairs;
     std::vector<uint32_t> perm;
 };
 
@@ -407,38 +407,46 @@ void* hs_tile_build(const float* xyz, int64_t n, double c) {
     std::vector<uint32_t> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
-    t->pts.resize(n); t->perm.resize(n);
-    for (int64_t i = 0; i < n; ++i) {
-        const uint32_t j = order[i], pi = (uint32_t)i;
-        float w;
+    const int64_t n_even = (n + 1) / 2 * 2;
+    t->pairs.resize(n_even); t->perm.resize(n);
+    float* rec = reinterpret_cast<float*>(t->pairs.data());
+    for (int64_t i = 0; i < n_even; ++i) {
+        float x = 3.0e38f, y = 3.0e38f, z = 3.0e38f, w;
+        uint32_t pi = 0xffffffffu;
+        if (i < n) { const uint32_t j = order[i]; x = xyz[3 * j]; y = xyz[3 * j + 1]; z = xyz[3 * j + 2]; pi = (uint32_t)i; t->perm[i] = j; }
         memcpy(&w, &pi, 4);
-        t->pts[i] = make_float4(xyz[3 * j], xyz[3 * j + 1], xyz[3 * j + 2], w);
-        t->perm[i] = j;
+        float* r = rec + (i >> 1) * 8 + (i & 1);
+        r[0] = x; r[2] = y; r[4] = z; r[6] = w;
     }
-    V.cs = t->cs.data(); V.pts = t->pts.data();
+    V.cs = t->cs.data(); V.pairs = t->pairs.data();
     return t;
 }
 void hs_tile_free(void* t) { delete (HostTile*)t; }
 
 // q: (m,3) queries already posed, processed in rows of 32 in the given order.  idx: caller index of
-// the match or -1; dist: its distance; stats[0] = passes, [1] = staged batches, [2] = global-path rows,
-// [3] = staged points, [4] = rows that used ring order
-void hs_tile_nn(void* tp, const float* qs, int64_t m, double max_dist, int cap, int cscap, int core_e, double hint,
+// the match or -1; dist: its distance; stats[0] = passes, [1] = staged pieces, [2] = rows scanned in
+// global memory, [3] = staged points, [5] = candidates evaluated
+// ng: groups per warp row (the kernel's NG): groups are independent, so a group of L = 32 / ng lanes
+// with its slice cap / ng of the stage buffer is replayed as a row of its own.
+void hs_tile_nn(void* tp, const float* qs, int64_t m, double max_dist, int cap, int core_e, double hint, int ng,
                 int64_t* idx, float* dist, int64_t* stats) {
     HostTile* t = (HostTile*)tp;
     const TileGrid& G = t->v;
     const float md = (float)max_dist, max_d2 = md * md;
     const float rmax = tile_rmax(G, max_d2);
+    g_tile_evals = 0;
     std::vector<float4> spts(cap);
-    std::vector<uint32_t> scs(cscap);
-    for (int64_t row0 = 0; row0 < m; row0 += 32) {
+    const uint32_t capp = ((uint32_t)cap >> 1) / (uint32_t)ng;
+    const int L = 32 / ng;
+    for (int64_t row0 = 0; row0 < m; row0 += L) {
         TileQuery q[32]; TileBest b[32]; bool valid[32]; float rl[32];
         uint32_t todo = 0;
-        for (int l = 0; l < 32; ++l) {
+        for (int l = 0; l < L; ++l) {
             const int64_t i = row0 + l;
             valid[l] = false;
             b[l].d2 = max_d2; b[l].pos = kTileNone; b[l].x = b[l].y = b[l].z = 0.f;
             q[l] = TileQuery{};
+            q[l].qx = q[l].qy = q[l].qz = NAN;
             if (i < m && qs[3 * i] == qs[3 * i])
                 valid[l] = tile_make_query(G, qs[3 * i], qs[3 * i + 1], qs[3 * i + 2], q[l]) && !tile_query_far_outside(G, q[l], max_d2);
             rl[l] = fminf(fmaxf((float)hint, 0.03125f), rmax);
@@ -449,13 +457,13 @@ void hs_tile_nn(void* tp, const float* qs, int64_t m, double max_dist, int cap, 
             const int leader = __builtin_ffs((int)todo) - 1;
             bool elig[32];
             float rho = 0.f;
-            for (int l = 0; l < 32; ++l) {
+            for (int l = 0; l < L; ++l) {
                 elig[l] = ((todo >> l) & 1u) && abs(q[l].ix - q[leader].ix) <= core_e && abs(q[l].iy - q[leader].iy) <= core_e &&
                           abs(q[l].iz - q[leader].iz) <= core_e;
                 if (elig[l]) rho = fmaxf(rho, rl[l]);
             }
             TileBox U{INT_MAX, INT_MIN, INT_MAX, INT_MIN, INT_MAX, INT_MIN};
-            for (int l = 0; l < 32; ++l) {
+            for (int l = 0; l < L; ++l) {
                 if (!elig[l]) continue;
                 U.x0 = std::min(U.x0, tile_cell_floor(q[l].gx - rho)); U.x1 = std::max(U.x1, tile_cell_floor(q[l].gx + rho));
                 U.y0 = std::min(U.y0, tile_cell_floor(q[l].gy - rho)); U.y1 = std::max(U.y1, tile_cell_floor(q[l].gy + rho));
@@ -463,66 +471,63 @@ void hs_tile_nn(void* tp, const float* qs, int64_t m, double max_dist, int cap, 
             }
             TileBox R{std::max(U.x0, 0), std::min(U.x1, G.nx - 1), std::max(U.y0, 0), std::min(U.y1, G.ny - 1), std::max(U.z0, 0), std::min(U.z1, G.nz - 1)};
             if (R.x0 <= R.x1 && R.y0 <= R.y1 && R.z0 <= R.z1) {
-                const int rnx = R.x1 - R.x0 + 1, rny = R.y1 - R.y0 + 1, rnz = R.z1 - R.z0 + 1, W = rnx + 1, nrows = rny * rnz;
-                const int RB = std::min(32, cscap / W);
+                const int rnx = R.x1 - R.x0 + 1, rny = R.y1 - R.y0 + 1, rnz = R.z1 - R.z0 + 1, nrows = rny * rnz;
                 int ra = 0;
                 while (ra < nrows) {
-                    uint32_t gs[32], len[32], incl[32]; size_t base[32]; bool rowv[32];
+                    uint32_t ps[32], lenp[32], incl[32];
                     uint32_t run = 0; int nfit = 0;
-                    for (int l = 0; l < 32; ++l) {
+                    for (int l = 0; l < L; ++l) {
                         const int r = ra + l;
-                        rowv[l] = l < RB && r < nrows;
-                        gs[l] = 0; len[l] = 0; base[l] = 0;
-                        if (rowv[l]) {
+                        ps[l] = 0; lenp[l] = 0;
+                        if (r < nrows) {
                             const int jz = R.z0 + r / rny, jy = R.y0 + r % rny;
-                            base[l] = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
-                            gs[l] = G.cs[base[l]]; len[l] = G.cs[base[l] + rnx] - gs[l];
+                            const size_t base = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
+                            const uint32_t gs = G.cs[base], ge = G.cs[base + rnx];
+                            if (ge > gs) { ps[l] = gs >> 1; lenp[l] = ((ge + 1u) >> 1) - ps[l]; }
                         }
-                        run += len[l]; incl[l] = run;
-                        if (rowv[l] && incl[l] <= (uint32_t)cap) nfit++;
+                        run += lenp[l]; incl[l] = run;
+                        if (r < nrows && incl[l] <= capp) nfit++;
                     }
                     if (nfit == 0) {
                         stats[2]++;
-                        const int jz = R.z0 + ra / rny, jy = R.y0 + ra % rny;
-                        const size_t gb = ((size_t)jz * G.ny + jy) * G.nx + R.x0;
-                        for (int l = 0; l < 32; ++l)
-                            if (elig[l]) tile_visit_row(G, q[l], b[l], jy, jz, R.x0, R.x1, G.cs + gb, G.pts, INT_MIN);
+                        const float4* gp = G.pairs + 2 * (size_t)ps[0];
+                        for (int l = 0; l < L; ++l) {            // every lane scans (same as the kernel): settled lanes cannot improve
+                            float best = b[l].d2;
+                            const uint32_t slot = tile_scan_pairs(gp, lenp[0], q[l], best);
+                            if (slot != kTileNone) tile_take(gp, slot, lenp[0], q[l], best, b[l]);
+                        }
                         ra += 1;
                         continue;
                     }
                     const uint32_t total = incl[nfit - 1];
                     if (total > 0) {
-                        stats[1]++; stats[3] += total;
-                        for (int l = 0; l < nfit; ++l) {
-                            const uint32_t excl = incl[l] - len[l];
-                            for (uint32_t k = 0; k < len[l]; ++k) spts[excl + k] = G.pts[gs[l] + k];
-                            for (int j = 0; j <= rnx; ++j) scs[l * W + j] = G.cs[base[l] + j] - gs[l] + excl;
-                        }
-                        const bool whole = ra == 0 && nfit == nrows;
-                        if (whole) stats[4]++;
-                        for (int l = 0; l < 32; ++l) {
-                            if (!elig[l]) continue;
-                            if (whole) tile_search_rings(G, q[l], b[l], R, ra, nfit, W, scs.data(), spts.data());
-                            else tile_search_linear(G, q[l], b[l], R, ra, nfit, W, scs.data(), spts.data());
+                        stats[1]++; stats[3] += 2 * total;
+                        for (int l = 0; l < nfit; ++l)
+                            for (uint32_t k = 0; k < 2 * lenp[l]; ++k) spts[2 * (incl[l] - lenp[l]) + k] = G.pairs[2 * (size_t)ps[l] + k];
+                        for (int l = 0; l < L; ++l) {
+                            float best = b[l].d2;
+                            const uint32_t slot = tile_scan_pairs(spts.data(), total, q[l], best);
+                            if (slot != kTileNone) tile_take(spts.data(), slot, total, q[l], best, b[l]);
                         }
                     }
                     ra += nfit;
                 }
             }
-            for (int l = 0; l < 32; ++l) {
+            for (int l = 0; l < L; ++l) {
                 if (!elig[l]) continue;
                 const bool settled = rho >= rmax || tile_settled(G, q[l], b[l], U);
                 if (settled) todo &= ~(1u << l);
-                else rl[l] = fminf(b[l].pos != kTileNone ? tile_radius_for(G, b[l]) : fmaxf(2.0f * rho, 1.0f), rmax);
+                else rl[l] = fminf(b[l].pos != kTileNone ? tile_radius_for(G, b[l]) : 2.0f * rho, rmax);
             }
         }
-        for (int l = 0; l < 32; ++l) {
+        for (int l = 0; l < L; ++l) {
             const int64_t i = row0 + l;
             if (i >= m) break;
             if (b[l].pos != kTileNone) { idx[i] = t->perm[b[l].pos]; dist[i] = sqrtf(b[l].d2); }
             else { idx[i] = -1; dist[i] = INFINITY; }
         }
     }
+    stats[5] = g_tile_evals;
 }
 
 uint64_t hs_box_mask(int x0, int x1, int y0, int y1, int z0, int z1) { return brick_box_mask(x0, x1, y0, y1, z0, z1); }

@@ -2,7 +2,7 @@
 exact nearest-neighbour search.
 
 tests/hostsim/_hostsim.so compiles the SAME per-lane functions the fused kernel uses; the warp glue
-(leader election, staged cell box, pieces of `cap` points, settle test, halo doubling) is restated
+(leader election, staged cell box, pieces of `cap` points, settle test, next radius) is restated
 with plain loops.  Every configuration must return the exact 1-NN within max_dist."""
 import ctypes as C
 import os
@@ -28,7 +28,7 @@ def hs():
     lib.hs_tile_build.restype = C.c_void_p
     lib.hs_tile_build.argtypes = [C.c_void_p, C.c_int64, C.c_double]
     lib.hs_tile_free.argtypes = [C.c_void_p]
-    lib.hs_tile_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double,
+    lib.hs_tile_nn.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_double, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
@@ -37,14 +37,14 @@ def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def tile_nn(lib, pts, q, c, max_dist, cap=256, cscap=512, core_e=4, hint=0.5):
+def tile_nn(lib, pts, q, c, max_dist, cap=384, core_e=8, hint=0.5, ng=4):
     pts = np.ascontiguousarray(pts, dtype=np.float32)
     q = np.ascontiguousarray(q, dtype=np.float32)
     t = lib.hs_tile_build(ptr(pts), len(pts), float(c))
     idx = np.empty(len(q), dtype=np.int64)
     dist = np.empty(len(q), dtype=np.float32)
     stats = np.zeros(8, dtype=np.int64)
-    lib.hs_tile_nn(t, ptr(q), len(q), float(max_dist), cap, cscap, core_e, float(hint), ptr(idx), ptr(dist), ptr(stats))
+    lib.hs_tile_nn(t, ptr(q), len(q), float(max_dist), cap, core_e, float(hint), ng, ptr(idx), ptr(dist), ptr(stats))
     lib.hs_tile_free(t)
     return idx, dist, stats
 
@@ -79,21 +79,6 @@ def sorted_queries(q, c):
     return q[np.argsort(key, kind="stable")]
 
 
-def test_ring_offsets_cover_each_ring_once(hs):
-    # python restatement of tile_ring_offset, checked for coverage (the C++ one is exercised by every search)
-    for k in range(1, 6):
-        s = 2 * k + 1
-        seen = set()
-        for e in range(8 * k):
-            if e < s: dz, dy = -k, e - k
-            elif e < 2 * s: dz, dy = k, e - s - k
-            elif e < 3 * s - 2: dy, dz = -k, e - 2 * s - k + 1
-            else: dy, dz = k, e - (3 * s - 2) - k + 1
-            assert max(abs(dy), abs(dz)) == k
-            seen.add((dy, dz))
-        assert len(seen) == 8 * k
-
-
 @pytest.mark.parametrize("disp", [0.0, 0.05, 0.4, 1.2])
 def test_slab_displaced(hs, disp):
     tgt = ds.make_urban_slab(40000, seed=5)
@@ -101,19 +86,20 @@ def test_slab_displaced(hs, disp):
     q = tgt + rng.normal(0, 0.005, tgt.shape).astype(np.float32)
     q = q + np.float32(disp) * np.array([0.6, -0.5, 0.62], dtype=np.float32)
     q = sorted_queries(q, 0.25)
-    st = check(hs, tgt, q, 0.25, 2.0, hint=0.25 if disp == 0.0 else 0.5)
-    if disp == 0.0:
-        assert st[0] <= 1.5 * (len(q) / 32)      # aligned scans settle in about one pass per row
+    for ng in (1, 4):
+        st = check(hs, tgt, q, 0.25, 2.0, hint=0.25 if disp == 0.0 else 0.5, ng=ng)
+        if disp == 0.0:
+            assert st[0] <= 1.5 * ng * (len(q) / 32)      # aligned scans settle in about one pass per group
 
 
-@pytest.mark.parametrize("cap,cscap,core_e,hint", [(256, 512, 4, 0.5), (16, 64, 1, 0.1), (4, 8, 0, 3.0), (256, 512, 4, 40.0), (64, 16, 2, 1.0)])
-def test_small_buffers_and_unsorted_queries(hs, cap, cscap, core_e, hint):
-    """Tiny stage buffers force the multi-piece and the global-memory row paths; unsorted queries
+@pytest.mark.parametrize("cap,core_e,hint,ng", [(256, 8, 0.5, 1), (384, 8, 0.5, 4), (16, 1, 0.1, 2), (8, 0, 3.0, 1), (256, 4, 40.0, 8), (64, 2, 1.0, 4)])
+def test_small_buffers_and_unsorted_queries(hs, cap, core_e, hint, ng):
+    """Tiny stage buffers force staging in pieces and the global-memory row path; unsorted queries
     force several leaders per row.  All exact."""
     rng = np.random.default_rng(7)
     tgt = rng.random((5000, 3)).astype(np.float32) * np.array([4, 3, 1], dtype=np.float32)
     q = rng.random((1500, 3)).astype(np.float32) * np.array([5, 4, 2], dtype=np.float32) - 0.5
-    st = check(hs, tgt, q, 0.2, 0.7, cap=cap, cscap=cscap, core_e=core_e, hint=hint)
+    st = check(hs, tgt, q, 0.2, 0.7, cap=cap, core_e=core_e, hint=hint, ng=ng)
     if cap <= 16:
         assert st[2] > 0 or st[1] > st[0]        # pieces or global rows were really used
 
@@ -128,7 +114,7 @@ def test_far_and_degenerate_queries(hs):
         tgt[:50],                                                          # exactly on target points
     ])
     check(hs, tgt, q, 0.1, 0.5)
-    check(hs, tgt, q, 0.1, 1e9, cap=64)                                    # unbounded max_dist
+    check(hs, tgt, q, 0.1, 1e9, cap=64, ng=2)                              # unbounded max_dist
     # duplicates and a single-point target
     dup = np.repeat(tgt[:20], 30, axis=0)
     check(hs, dup, q, 0.1, 2.0, cap=16)
