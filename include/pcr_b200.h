@@ -117,6 +117,13 @@ int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort);
  * pcr_set_scan when the grid does not exist yet.  T = NULL means identity. */
 int pcr_set_scan_posed(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, const double T[16], int method);
 
+/* Device-resident inputs are read on the context's own (non-blocking) stream: before passing a
+ * device pointer that another stream may still be writing, order the two.  has_stream = 1: wait
+ * for `stream` (the "stream" entry of __cuda_array_interface__ v3: 1 = legacy default, 2 = per-thread
+ * default, else a cudaStream_t); has_stream = 0: wait for the whole device.  The Python layer calls
+ * this for every GPU array it is handed. */
+int pcr_sync_producer(pcr_ctx* ctx, int has_stream, void* stream);
+
 /* ---- per iteration --------------------------------------------------------------------- */
 
 /* One linearisation at transform T: SE(3) transform of the scan, exact correspondence
@@ -174,6 +181,9 @@ int pcr_comm_unique_id(void* id128);
  * pcr_linearize / pcr_align all-reduce the 29-double record (ncclSum, float64). */
 int pcr_comm_init_rank(pcr_ctx* ctx, int nranks, int rank, const void* id128);
 int pcr_comm_destroy(pcr_ctx* ctx);
+/* Hand the communicator of `src` over to `dst` (same device): a registration object whose target is
+ * replaced gets a NEW context, and an NCCL unique id cannot be used twice.  `src` becomes single-GPU. */
+int pcr_comm_move(pcr_ctx* dst, pcr_ctx* src);
 
 /* ---- instrumentation -------------------------------------------------------------------- */
 

@@ -52,6 +52,8 @@ SYMBOLS = {
     "pcr_comm_unique_id": (_i, [_vp]),
     "pcr_comm_init_rank": (_i, [_vp, _i, _i, _vp]),
     "pcr_comm_destroy": (_i, [_vp]),
+    "pcr_comm_move": (_i, [_vp, _vp]),
+    "pcr_sync_producer": (_i, [_vp, _i, _vp]),
     "pcr_last_kernel_ms": (_i, [_vp, _pf]),
     "pcr_launch_count": (_i, [_vp, _pi64]),
     "pcr_stream": (_i, [_vp, C.POINTER(_vp)]),
@@ -117,6 +119,7 @@ class DevicePoints:
         if cai.get("strides") not in (None, (3 * int(typestr[2]), int(typestr[2]))):
             raise ValueError(f"{name}: device arrays must be C-contiguous")
         self.obj = obj                      # keeps the memory alive
+        self.stream = cai.get("stream")     # producer stream (interface v3) or None
         self.ptr = int(cai["data"][0])
         self.shape = shape
         self.dtype = np.dtype(typestr)
@@ -188,8 +191,19 @@ class Context:
         except Exception:
             pass
 
+    def _order_after_producer(self, *arrays):
+        """GPU arrays are read on this context's own non-blocking stream: wait for whoever produced
+        them first (their __cuda_array_interface__ stream if they name one, else the whole device)."""
+        for a in arrays:
+            if isinstance(a, DevicePoints):
+                if a.stream is None:
+                    self._check(self._lib.pcr_sync_producer(self._h, 0, None))
+                else:
+                    self._check(self._lib.pcr_sync_producer(self._h, 1, C.c_void_p(int(a.stream))))
+
     # -- target side --------------------------------------------------------------------
     def set_target_points(self, pts_f32):
+        self._order_after_producer(pts_f32)
         self._check(self._lib.pcr_set_target_points(self._h, _ptr(pts_f32), pts_f32.shape[0]))
 
     def build_nn_index(self):
@@ -202,6 +216,7 @@ class Context:
         self._check(self._lib.pcr_estimate_normals(self._h, int(k)))
 
     def set_normals(self, nrm_f32):
+        self._order_after_producer(nrm_f32)
         self._check(self._lib.pcr_set_normals(self._h, _ptr(nrm_f32)))
 
     def get_normals(self, n):
@@ -223,6 +238,7 @@ class Context:
 
     def build_voxels(self, pts, voxel_size, min_points, with_icov=True):
         arr, is64 = self._f32_or_f64(pts)
+        self._order_after_producer(arr)
         self._check(self._lib.pcr_build_voxels(self._h, _ptr(arr), arr.shape[0], is64, float(voxel_size),
                                                int(min_points), int(bool(with_icov))))
 
@@ -247,6 +263,7 @@ class Context:
         by T when that grid exists, else along a Morton curve); False/0 keep order; -1 keep order,
         caller promises spatial coherence."""
         Tp = None if T is None else np.ascontiguousarray(T, dtype=np.float64)
+        self._order_after_producer(pts_f32)
         self._check(self._lib.pcr_set_scan_posed(self._h, _ptr(pts_f32), pts_f32.shape[0], int(sort), _ptr(Tp), int(method)))
 
     def set_voxel_lists(self, enable):
@@ -319,6 +336,7 @@ class Context:
     # -- utilities ------------------------------------------------------------------------
     def knn(self, q_f32, k):
         m = q_f32.shape[0]
+        self._order_after_producer(q_f32)
         dist = np.empty((m, k), dtype=np.float32)
         idx = np.empty((m, k), dtype=np.int64)
         self._check(self._lib.pcr_knn(self._h, _ptr(q_f32), m, int(k), _ptr(dist), _ptr(idx)))
@@ -326,6 +344,7 @@ class Context:
 
     def voxel_query(self, q_f32):
         m = q_f32.shape[0]
+        self._order_after_producer(q_f32)
         vidx = np.empty(m, dtype=np.int64)
         dist = np.empty(m, dtype=np.float64)
         self._check(self._lib.pcr_voxel_query(self._h, _ptr(q_f32), m, _ptr(vidx), _ptr(dist)))
@@ -333,6 +352,7 @@ class Context:
 
     def voxel_filter(self, pts, voxel_size):
         arr, is64 = self._f32_or_f64(pts)
+        self._order_after_producer(arr)
         out = np.empty((arr.shape[0], 3), dtype=np.float32)
         n_out = C.c_int64(0)
         self._check(self._lib.pcr_voxel_filter(self._h, _ptr(arr), arr.shape[0], is64, float(voxel_size), _ptr(out),
@@ -342,6 +362,7 @@ class Context:
     def voxel_labels(self, pts, voxel_size):
         """(labels (N,) int64, voxel coordinates (V,3) int32): voxel membership of every point."""
         arr, is64 = self._f32_or_f64(pts)
+        self._order_after_producer(arr)
         labels = np.empty(arr.shape[0], dtype=np.int64)
         coords = np.empty((arr.shape[0], 3), dtype=np.int32)
         nv = C.c_int64(0)
@@ -362,6 +383,10 @@ class Context:
     def comm_init_rank(self, nranks, rank, uid):
         buf = C.create_string_buffer(bytes(uid), 128)
         self._check(self._lib.pcr_comm_init_rank(self._h, int(nranks), int(rank), buf))
+
+    def comm_adopt(self, other):
+        """Take over the communicator of another context on the same GPU (see pcr_comm_move)."""
+        self._check(self._lib.pcr_comm_move(self._h, other._h))
 
     def comm_destroy(self):
         self._check(self._lib.pcr_comm_destroy(self._h))

@@ -1087,6 +1087,31 @@ int pcr_comm_init_rank(pcr_ctx* ctx, int nranks, int rank, const void* id128) {
     return PCR_OK;
 }
 
+int pcr_comm_move(pcr_ctx* dst, pcr_ctx* src) {
+    if (!dst || !src) return PCR_ERR_ARG;
+    if (dst == src) return PCR_OK;
+    if (dst->device != src->device) return fail(dst, PCR_ERR_ARG, "pcr_comm_move: contexts live on different devices");
+    cudaSetDevice(src->device);
+    if (src->stream) cudaStreamSynchronize(src->stream);      // no collective of the old context may still be in flight
+    pcr_comm_destroy(dst);
+    dst->nccl_comm = src->nccl_comm; dst->nranks = src->nranks; dst->rank = src->rank;
+    src->nccl_comm = nullptr; src->nranks = 1; src->rank = 0;
+    return PCR_OK;
+}
+
+int pcr_sync_producer(pcr_ctx* ctx, int has_stream, void* stream) {
+    if (!ctx) return PCR_ERR_ARG;
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    if (has_stream) {
+        // __cuda_array_interface__ v3: 1 = legacy default stream, 2 = per-thread default stream, else a cudaStream_t
+        cudaStream_t s = stream == (void*)1 ? cudaStreamLegacy : (stream == (void*)2 ? cudaStreamPerThread : (cudaStream_t)stream);
+        PCR_CUDA(cudaStreamSynchronize(s));
+    } else {
+        PCR_CUDA(cudaDeviceSynchronize());
+    }
+    return PCR_OK;
+}
+
 int pcr_comm_destroy(pcr_ctx* ctx) {
     if (!ctx) return PCR_ERR_ARG;
     if (ctx->nccl_comm && g_nccl.CommDestroy) {

@@ -22,4 +22,4 @@ class ICP(Registration):
         self.target = self.kdtree.data
         self._ctx = self.kdtree._ctx
         self._ctx.build_correspondence_lists()           # shell lists streamed by the correspondence pass
-        self._is_target_set = True
+        self._target_ready()

@@ -19,4 +19,4 @@ class NDT(Registration):
         self.voxels.set_points(target)
         self.voxels.calc_icov()
         self._ctx = self.voxels._ctx
-        self._is_target_set = True
+        self._target_ready()

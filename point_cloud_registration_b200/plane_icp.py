@@ -38,7 +38,7 @@ class PlaneICP(Registration):
                 raise ValueError("norm must have one row per target point")
             self._ctx.set_normals(nrm)
             self._normal = norm
-        self._is_target_set = True
+        self._target_ready()
 
     @property
     def normal(self):

@@ -22,6 +22,8 @@ class Registration:
         self._is_target_set = False
         self._ctx = None
         self._dist = None          # (rank, world_size) once attach_communicator() was called
+        self._comm_ctx = None      # context that currently owns the NCCL communicator
+        self._scan_generation = 0  # bumped by every upload: older UploadedScan handles are refused
         self.scan_is_presharded = False   # multi-GPU: scans passed in are already this rank's tile
         self.sort_scan = True      # Morton-sort the scan on upload in align()
         self.sort_scan_on_calc = os.environ.get("PCR_SORT_ON_CALC", "1") != "0"   # ... and in calc_H_g_e2(T, array)
@@ -31,6 +33,16 @@ class Registration:
     # -- reference surface --------------------------------------------------------------
     def is_target_set(self):
         return self._is_target_set
+
+    def _target_ready(self):
+        """Called by every set_target() once self._ctx holds the new target structures.  A
+        communicator attached earlier belongs to the PREVIOUS context: re-attach it, otherwise the
+        scan would still be sharded while the records are no longer all-reduced."""
+        self._is_target_set = True
+        self._scan_generation += 1          # the resident scan lived in the previous context
+        if self._dist is not None and self._comm_ctx is not self._ctx:
+            self._ctx.comm_adopt(self._comm_ctx)      # an NCCL id cannot be used twice: move the communicator itself
+            self._comm_ctx = self._ctx
 
     def set_target(self, target):
         raise NotImplementedError("set_target is not implemented.")
@@ -51,8 +63,8 @@ class Registration:
             raise ValueError("Target is not set.")
         if not isinstance(source, UploadedScan):
             self._upload(source, sort=self.sort_scan_on_calc, T=cur_T)
-        elif source.owner is not self:
-            raise ValueError("scan handle belongs to another registration object")
+        else:
+            self._check_handle(source)
         rec = self._ctx.linearize(self.method, np.asarray(cur_T, dtype=np.float64), self.max_dist)
         H, g, e2, self.last_inliers = _lib.record_to_H_g_e2(rec)
         return H, g, e2
@@ -63,8 +75,8 @@ class Registration:
         cur_T = np.asarray(init_T, dtype=np.float64)
         if not isinstance(source, UploadedScan):
             source = self.upload_scan(source, T=cur_T)
-        elif source.owner is not self:
-            raise ValueError("scan handle belongs to another registration object")
+        else:
+            self._check_handle(source)
         if device_loop is None:
             device_loop = not verbose
         if device_loop:
@@ -93,7 +105,13 @@ class Registration:
         per-call host->device copy the array form implies).  ``T``: the pose the iterations will
         start from (default identity); it only steers the on-device ordering of the scan."""
         self._upload(source, sort=self.sort_scan if sort is None else sort, T=T)
-        return UploadedScan(self)
+        return UploadedScan(self, self._scan_generation)
+
+    def _check_handle(self, handle):
+        if handle.owner is not self:
+            raise ValueError("scan handle belongs to another registration object")
+        if handle.generation != self._scan_generation:
+            raise ValueError("stale scan handle: another scan was uploaded (or the target was replaced) after it was created")
 
     def _upload(self, source, sort, T=None):
         if self._ctx is None:
@@ -104,6 +122,7 @@ class Registration:
             lo, hi = shard_bounds(src.shape[0], *self._dist)
             src = src[lo:hi]
         self._ctx.set_scan(src, sort=sort, T=T, method=self.method)
+        self._scan_generation += 1
 
     def attach_communicator(self, rank, world_size, unique_id):
         """Multi-GPU: this process owns one GPU and one contiguous tile of every scan; the
@@ -112,11 +131,14 @@ class Registration:
             raise ValueError("Target is not set.")
         self._ctx.comm_init_rank(world_size, rank, unique_id)
         self._dist = (rank, world_size)
+        self._comm_ctx = self._ctx
 
 
 class UploadedScan:
-    """Handle to the scan currently resident on the GPU of one registration object."""
-    __slots__ = ("owner",)
+    """Handle to the scan resident on the GPU of one registration object.  Only the LATEST upload
+    is resident: a handle is refused once another scan was uploaded after it."""
+    __slots__ = ("owner", "generation")
 
-    def __init__(self, owner):
+    def __init__(self, owner, generation):
         self.owner = owner
+        self.generation = generation

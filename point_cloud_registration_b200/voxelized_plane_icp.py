@@ -19,4 +19,4 @@ class VPlaneICP(Registration):
         self.voxels = VoxelGrid(self.voxel_size, device=self._device)
         self.voxels.set_points(target)
         self._ctx = self.voxels._ctx
-        self._is_target_set = True
+        self._target_ready()
