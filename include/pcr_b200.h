@@ -127,8 +127,8 @@ int pcr_sync_producer(pcr_ctx* ctx, int has_stream, void* stream);
 /* ---- per iteration --------------------------------------------------------------------- */
 
 /* One linearisation at transform T: SE(3) transform of the scan, exact correspondence
- * search, residual + Jacobian, reduction to the normal equations -- one fused kernel on the
- * default (tile stream) path, a correspondence and an accumulate kernel on the list path.
+ * search, residual + Jacobian, reduction to the normal equations -- a correspondence and an
+ * accumulate kernel on the default (list) path, one fused kernel on the tile-stream path.
  * Replaces ICP/PlaneICP/VPlaneICP/NDT.calc_H_g_e2 (icp.py:24, plane_icp.py:30,
  * voxelized_plane_icp.py:23, ndt.py:24).  With a communicator attached (pcr_comm_init_rank)
  * the record is summed over all ranks before it is returned. */
@@ -208,12 +208,17 @@ int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
 int pcr_set_shell_lists(pcr_ctx* ctx, int enable);
 int pcr_shell_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries, double* margin_cells);
 /* Which implementation of the per-iteration path runs (both exact, same results up to float64
- * summation order): 0 = tile stream (default): one fused kernel per linearisation; every warp
- * stages the cell box around its 32 scan points from a row-major dense grid into shared memory with
- * cp.async.bulk and searches it there (csrc/pcr_tile.cuh, pcr_tile_kernel.cuh); 1 = round-1 list
- * kernels (shell lists / voxel candidate lists + separate accumulate kernel), kept for A/B.
+ * summation order):
+ *   0 = list stream (default): correspondences from per-cell shell lists / voxel candidate lists
+ *       (correspond kernel) + accumulate kernel;
+ *   1 = tile stream: one fused kernel per linearisation; every warp stages the cell box around its
+ *       32 scan points from a row-major dense grid into shared memory with cp.async.bulk (TMA engine,
+ *       mbarrier completion) and every lane scans every staged candidate with packed f32x2 arithmetic
+ *       (csrc/pcr_tile.cuh, pcr_tile_kernel.cuh).  Needs no per-point list structure (16 B per target
+ *       point instead of ~1.4 KB) but is measured 1.6-2x slower per iteration on the round-2 workloads
+ *       (profiles/r2_notes.md); kept selectable for targets whose lists do not fit.
  * Structures are built for the path that is selected when set_target runs: choose it right after
- * pcr_create (or with PCR_PATH=lists in the environment). */
+ * pcr_create (or with PCR_PATH=tile in the environment). */
 int pcr_set_path(pcr_ctx* ctx, int path);
 /* Row grid of the tile-stream path (which: 0 target points, 1 kept voxel means): cell edge, number
  * of cells of the dense table, occupied cells, bytes of the whole structure. */

@@ -283,8 +283,8 @@ class Context:
         return dict(band_cells=a.value, entries=b.value, margin_cells=m.value, bytes=b.value * 17)
 
     def set_path(self, path):
-        """'tile' (default) or 'lists' (round-1 kernels); call before set_target builds its structures."""
-        self._check(self._lib.pcr_set_path(self._h, {"tile": 0, "lists": 1}[path] if isinstance(path, str) else int(path)))
+        """'lists' (default) or 'tile' (tile-stream kernel); call before set_target builds its structures."""
+        self._check(self._lib.pcr_set_path(self._h, {"lists": 0, "tile": 1}[path] if isinstance(path, str) else int(path)))
 
     def set_record_matches(self, enable):
         self._check(self._lib.pcr_set_record_matches(self._h, int(bool(enable))))

@@ -1388,14 +1388,17 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_CELL_ORDER")) ctx->cell_order = atoi(e) != 0;
     if (const char* e = getenv("PCR_GRAB_ROWS")) ctx->grab_rows = atoi(e) >= 0 && atoi(e) <= 64 ? atoi(e) : 0;
     if (const char* e = getenv("PCR_SPLIT")) ctx->split_passes = atoi(e) != 0;
-    if (const char* e = getenv("PCR_PATH")) ctx->use_tile = strcmp(e, "lists") != 0;
+    if (const char* e = getenv("PCR_PATH")) ctx->use_tile = strcmp(e, "tile") == 0;
     if (const char* e = getenv("PCR_TILE_PPC")) ctx->tile_ppc_tgt = atof(e) > 0.25 ? atof(e) : 8.0;
     if (const char* e = getenv("PCR_TILE_PPC_VOX")) ctx->tile_ppc_vox = atof(e) > 0.25 ? atof(e) : 4.0;
     if (const char* e = getenv("PCR_TILE_CAP")) ctx->tile_cap = atoi(e) >= 256 && atoi(e) <= 4096 ? atoi(e) / 64 * 64 : 384;
     if (const char* e = getenv("PCR_TILE_CORE")) ctx->tile_core_e = atoi(e) >= 0 && atoi(e) <= 16 ? atoi(e) : 8;
-    if (const char* e = getenv("PCR_TILE_MINB")) ctx->tile_min_blocks = atoi(e) >= 3 && atoi(e) <= 4 ? atoi(e) : 0;
+    if (const char* e = getenv("PCR_TILE_MINB")) ctx->tile_min_blocks = atoi(e) >= 3 && atoi(e) <= 6 ? atoi(e) : 0;
     if (const char* e = getenv("PCR_TILE_R0")) ctx->tile_first_radius = atof(e) > 0.0 ? (float)atof(e) : 0.5f;
-    if (const char* e = getenv("PCR_TILE_G")) ctx->tile_groups = (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8) ? atoi(e) : 4;
+    if (const char* e = getenv("PCR_TILE_G")) ctx->tile_groups = (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8) ? atoi(e) : 1;
+    if (const char* e = getenv("PCR_ACC_MINB")) ctx->acc_min_blocks = atoi(e) == 3 ? 3 : 2;
+    if (const char* e = getenv("PCR_TILE_BULK_MIN")) ctx->tile_bulk_min = atoi(e) >= 1 ? atoi(e) : 9;
+    if (const char* e = getenv("PCR_TILE_SPLIT")) ctx->tile_split = atoi(e) != 0;
     if (const char* e = getenv("PCR_TILE_KR")) ctx->tile_rows_per_unit = atoi(e) == 2 || atoi(e) == 4 ? atoi(e) : 0;
     int rc = ensure_loop_buffers(ctx);
     if (rc) { std::string m = ctx->err; pcr_destroy(ctx); return fail(nullptr, rc, m); }
@@ -1676,8 +1679,8 @@ int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries) {
 
 int pcr_set_path(pcr_ctx* ctx, int path) {
     if (!ctx) return PCR_ERR_ARG;
-    if (path != 0 && path != 1) return fail(ctx, PCR_ERR_ARG, "pcr_set_path: 0 = tile stream, 1 = lists");
-    ctx->use_tile = path == 0;
+    if (path != 0 && path != 1) return fail(ctx, PCR_ERR_ARG, "pcr_set_path: 0 = lists, 1 = tile stream");
+    ctx->use_tile = path == 1;
     return PCR_OK;
 }
 

@@ -14,7 +14,7 @@
 #define PCR_ACC_BATCH 2
 #endif
 #ifndef PCR_ACC_MINB
-#define PCR_ACC_MINB 3
+#define PCR_ACC_MINB 2
 #endif
 
 namespace pcr {
@@ -115,17 +115,20 @@ struct pcr_ctx {
     pcr::DevBuf vox_rec_ndt;      // float4[3n]: (mean, W00), (W01, W02, W11, W12), (W22, 0, 0, 0)
     bool has_voxels = false, has_icov = false;
 
-    // ---- tile-stream path (default hot path; see pcr_tile.cuh) ----
+    // ---- tile-stream path (alternative hot path, PCR_PATH=tile / pcr_set_path; see pcr_tile.cuh) ----
     pcr::TileIndex tile_tgt;      // over the target points (ICP / PlaneICP)
     pcr::TileIndex tile_vox;      // over the kept voxel means (VPlaneICP / NDT)
-    int use_tile = 1;             // 1: tile-stream kernel, 0: round-1 list kernels (A/B, PCR_PATH=lists)
+    int use_tile = 0;             // 0: list kernels (default: faster on every measured workload), 1: tile-stream kernel (PCR_PATH=tile)
     double tile_ppc_tgt = 8.0;    // desired mean points per occupied cell of the row grids
     double tile_ppc_vox = 4.0;
     int tile_cap = 384;           // points a warp can stage at once
     int tile_core_e = 8;          // lanes farther than this many cells from the leader wait for their own pass
     int tile_min_blocks = 0;      // resident blocks per SM requested (0: default)
     int tile_rows_per_unit = 0;   // warp rows per unit of work (2 or 4; 0: chosen from the scan size)
-    int tile_groups = 4;          // independent groups a warp row is searched as (1, 2, 4, 8; see tile_search_row)
+    int acc_min_blocks = 2;       // resident blocks per SM requested for the accumulate kernel (2: 128 registers, 3: 80)
+    int tile_bulk_min = 9;        // staging: ranges of at least this many pair records (32 B each) go through the TMA engine
+    int tile_split = 0;           // 1: correspondences and accumulation as two kernels (A/B, PCR_TILE_SPLIT)
+    int tile_groups = 1;          // independent groups a warp row is searched as (1, 2, 4, 8; see tile_search_row)
     int record_matches = 0;       // 1: the tile kernel also parks the matched positions (pcr_debug_matches)
     long long normals_epoch = 0;
     float tile_first_radius = 0.5f;   // halo radius (cells) a new scan starts with

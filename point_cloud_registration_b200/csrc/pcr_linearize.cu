@@ -291,34 +291,33 @@ __device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32
 }
 
 // ---- pass 2: residual + Jacobian terms of the parked correspondences, reduction, GN step ----------
+// Every thread owns FOUR consecutive scan slots per trip: one 16-byte load each for the parked
+// positions and the three scan coordinates (instead of sixteen scalar loads: the pass used to be
+// bound by the load/store queue, ncu lg_throttle 2.7 per issue), then the four matched records are
+// requested together (the gathers are latency bound) before the first is consumed.  Terms are added
+// in slot order: the summation order is fixed.
 template <int METHOD>
 __device__ __forceinline__ void accumulate_pass(const LinParams& P, BlockShared& sh, const Pose32& pose) {
     constexpr int NACC = NAcc<METHOD>::value;
+    const long long quads = P.n_pad >> 2;                        // n_pad is a multiple of 32
     const long long stride = (long long)gridDim.x * kLinThreads;
-    const long long first = blockIdx.x * (long long)kLinThreads + threadIdx.x;
     float acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
-    // kAccBatch slots per trip: positions, scan points and matched records of all of them are
-    // requested before the first is consumed (the gathers are latency bound); the terms are added
-    // in slot order, so the per-thread summation order does not depend on the batching
-    for (long long i = first; i < P.n_pad; i += kAccBatch * stride) {
-        int pos[kAccBatch];
-        float px[kAccBatch], py[kAccBatch], pz[kAccBatch];
-        MatchRec rec[kAccBatch];
+    const int4* prev4 = reinterpret_cast<const int4*>(P.prev);
+    const float4* sx4 = reinterpret_cast<const float4*>(P.sx);
+    const float4* sy4 = reinterpret_cast<const float4*>(P.sy);
+    const float4* sz4 = reinterpret_cast<const float4*>(P.sz);
+    for (long long t = blockIdx.x * (long long)kLinThreads + threadIdx.x; t < quads; t += stride) {
+        const int4 pq = prev4[t];
+        const int pos[4] = {pq.x, pq.y, pq.z, pq.w};
+        MatchRec rec[4];
 #pragma unroll
-        for (int u = 0; u < kAccBatch; ++u) {
-            const long long iu = i + u * stride;
-            pos[u] = iu < P.n_pad ? P.prev[iu] : -1;
-        }
+        for (int u = 0; u < 4; ++u) fetch_match<METHOD>(P, pos[u], rec[u]);
+        const float4 X = __ldg(sx4 + t), Y = __ldg(sy4 + t), Z = __ldg(sz4 + t);
+        const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
 #pragma unroll
-        for (int u = 0; u < kAccBatch; ++u) {
-            const long long iu = i + u * stride;
-            if (pos[u] >= 0) { px[u] = __ldg(P.sx + iu); py[u] = __ldg(P.sy + iu); pz[u] = __ldg(P.sz + iu); }
-            fetch_match<METHOD>(P, pos[u], rec[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < kAccBatch; ++u)
+        for (int u = 0; u < 4; ++u)
             if (pos[u] >= 0) accumulate_match<METHOD>(pose, acc, rec[u], px[u], py[u], pz[u]);
     }
     reduce_and_finish<METHOD>(P, sh, acc);
@@ -333,8 +332,8 @@ __global__ void __launch_bounds__(kLinThreads, MINB) correspond_kernel(const Lin
     correspond_pass<METHOD, true>(P, pose);
 }
 
-template <int METHOD>
-__global__ void __launch_bounds__(kLinThreads, kAccMinBlocks) accumulate_kernel(const LinParams P) {
+template <int METHOD, int MINB>
+__global__ void __launch_bounds__(kLinThreads, MINB) accumulate_kernel(const LinParams P) {
     __shared__ BlockShared sh;
     Pose32 pose;
     if (!load_pose(P, sh, pose)) return;
@@ -635,6 +634,21 @@ static int blocks_for_kernel(pcr_ctx* ctx, K kernel, int& cached, long long n_pa
 }
 
 template <int METHOD>
+static int launch_accumulate(pcr_ctx* ctx, const LinParams& P) {
+    int* cache = ctx->lin_blocks_per_sm[METHOD];
+    // quads of slots per thread: the grid only needs a quarter of the threads
+    if (ctx->acc_min_blocks == 3) {
+        const int blocks = blocks_for_kernel(ctx, accumulate_kernel<METHOD, 3>, cache[0], (P.n_pad + 3) / 4);
+        accumulate_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
+    } else {
+        const int blocks = blocks_for_kernel(ctx, accumulate_kernel<METHOD, 2>, cache[1], (P.n_pad + 3) / 4);
+        accumulate_kernel<METHOD, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
+    }
+    PCR_LAUNCH_CHECK();
+    return PCR_OK;
+}
+
+template <int METHOD>
 static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     // ctx->min_blocks = resident blocks per SM requested for the correspondence pass (2..6)
     // resident blocks per SM of the correspondence kernel: measured best 5 (48 registers) for the
@@ -651,10 +665,7 @@ static int launch_method(pcr_ctx* ctx, const LinParams& P) {
             default: blocks = blocks_for_kernel(ctx, correspond_kernel<METHOD, 6>, cache[6], P.n_pad); correspond_kernel<METHOD, 6><<<blocks, kLinThreads, 0, ctx->stream>>>(P); break;
         }
         PCR_LAUNCH_CHECK();
-        blocks = blocks_for_kernel(ctx, accumulate_kernel<METHOD>, cache[0], P.n_pad);
-        accumulate_kernel<METHOD><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
-        PCR_LAUNCH_CHECK();
-        return PCR_OK;
+        return launch_accumulate<METHOD>(ctx, P);
     }
     const int blocks = blocks_for_kernel(ctx, linearize_fused_kernel<METHOD, 3>, cache[7], P.n_pad);
     linearize_fused_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
@@ -684,9 +695,28 @@ static int launch_tile_kernel(pcr_ctx* ctx, const LinParams& P, const TileParams
     return PCR_OK;
 }
 
+template <int MINB, int NG>
+static int launch_tile_correspond(pcr_ctx* ctx, const LinParams& P, const TileParams& TP, int& cached_blocks) {
+    const size_t smem = (size_t)TP.warp_bytes * (kLinThreads / 32);
+    auto kernel = tile_correspond_kernel<MINB, NG>;
+    if (cached_blocks == 0) {
+        PCR_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, kLinThreads, smem) != cudaSuccess || nb < 1) { cudaGetLastError(); nb = 1; }
+        cached_blocks = nb;
+    }
+    const long long rows = P.n_pad / 32;
+    long long want = (rows + kLinThreads / 32 - 1) / (kLinThreads / 32);
+    long long cap = (long long)ctx->sm_count * cached_blocks;
+    if (cap > kMaxLinBlocks) cap = kMaxLinBlocks;
+    if (want < 1) want = 1;
+    kernel<<<(int)(want < cap ? want : cap), kLinThreads, smem, ctx->stream>>>(P, TP);
+    PCR_LAUNCH_CHECK();
+    return PCR_OK;
+}
+
 template <int METHOD, int KR, int NG>
 static int launch_tile_minb(pcr_ctx* ctx, const LinParams& P, const TileParams& TP, int& cached_blocks) {
-    if (ctx->tile_min_blocks == 4) return launch_tile_kernel<METHOD, 4, KR, NG>(ctx, P, TP, cached_blocks);
     return launch_tile_kernel<METHOD, 3, KR, NG>(ctx, P, TP, cached_blocks);
 }
 
@@ -701,11 +731,23 @@ static int launch_tile(pcr_ctx* ctx, const LinParams& P) {
     TP.perm = t.perm.as<uint32_t>();
     TP.match_out = ctx->record_matches ? ctx->scan_prev.as<int>() : nullptr;
     TP.cap = ctx->tile_cap;
+    TP.bulk_min = ctx->tile_bulk_min;
     TP.rmax = tile_rmax(t.view, P.max_d2);
     TP.core_e = ctx->tile_core_e;
     constexpr int KRMAX = 4;                       // match slots reserved per warp: [KRMAX][32] float4
     TP.warp_bytes = (int)(((size_t)TP.cap * 16 + 16 + (size_t)KRMAX * 32 * 16 + 127) / 128 * 128);
     int* cache = ctx->lin_blocks_per_sm[METHOD];
+    if (ctx->tile_split) {
+        // correspondences (method independent), then the accumulate kernel of the list path on the parked positions
+        TP.match_out = ctx->scan_prev.as<int>();
+        TP.warp_bytes = (int)(((size_t)TP.cap * 16 + 16 + 127) / 128 * 128);
+        int rc;
+        const int mb = ctx->tile_min_blocks > 0 ? ctx->tile_min_blocks : 5;
+        if (ctx->tile_groups == 4) rc = mb >= 6 ? launch_tile_correspond<6, 4>(ctx, P, TP, cache[11]) : (mb == 5 ? launch_tile_correspond<5, 4>(ctx, P, TP, cache[11]) : launch_tile_correspond<4, 4>(ctx, P, TP, cache[11]));
+        else rc = mb >= 6 ? launch_tile_correspond<6, 1>(ctx, P, TP, cache[11]) : (mb == 5 ? launch_tile_correspond<5, 1>(ctx, P, TP, cache[11]) : launch_tile_correspond<4, 1>(ctx, P, TP, cache[11]));
+        if (rc) return rc;
+        return launch_accumulate<METHOD>(ctx, P);
+    }
     // rows per unit of work: 4 when every warp still gets many units, 2 for small scans (less tail)
     const long long rows = P.n_pad / 32;
     const bool big = ctx->tile_rows_per_unit > 0 ? ctx->tile_rows_per_unit >= 4 : rows >= (long long)ctx->sm_count * 32 * 4 * 8;
@@ -714,14 +756,12 @@ static int launch_tile(pcr_ctx* ctx, const LinParams& P) {
         switch (ng) {
             case 1: return launch_tile_minb<METHOD, 4, 1>(ctx, P, TP, cache[8]);
             case 2: return launch_tile_minb<METHOD, 4, 2>(ctx, P, TP, cache[8]);
-            case 8: return launch_tile_minb<METHOD, 4, 8>(ctx, P, TP, cache[8]);
             default: return launch_tile_minb<METHOD, 4, 4>(ctx, P, TP, cache[8]);
         }
     }
     switch (ng) {
         case 1: return launch_tile_minb<METHOD, 2, 1>(ctx, P, TP, cache[9]);
         case 2: return launch_tile_minb<METHOD, 2, 2>(ctx, P, TP, cache[9]);
-        case 8: return launch_tile_minb<METHOD, 2, 8>(ctx, P, TP, cache[9]);
         default: return launch_tile_minb<METHOD, 2, 4>(ctx, P, TP, cache[9]);
     }
 }
@@ -730,7 +770,7 @@ static int launch_linearize(pcr_ctx* ctx, int method, LinParams& P) {
     if (ctx->use_tile) {
         int rc = ensure_tile_index(ctx, method);
         if (rc) return rc;
-        ctx->prev_which = ctx->record_matches ? ((method == PCR_ICP || method == PCR_PLANE) ? 0 : 1) : -1;
+        ctx->prev_which = (ctx->record_matches || ctx->tile_split) ? ((method == PCR_ICP || method == PCR_PLANE) ? 0 : 1) : -1;
         switch (method) {
             case PCR_ICP: return launch_tile<PCR_METHOD_ICP>(ctx, P);
             case PCR_PLANE: return launch_tile<PCR_METHOD_PLANE>(ctx, P);

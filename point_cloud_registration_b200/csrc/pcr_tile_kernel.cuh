@@ -25,6 +25,7 @@ struct TileParams {
     const uint32_t* perm;     // position -> position in the source index (only for match_out)
     int* match_out;           // optional [n_pad]: matched source position per scan slot (-1 none)
     int cap;                  // points per warp stage buffer
+    int bulk_min;             // ranges of at least this many pair records are bulk copies (TMA); shorter ones are copied by their lane
     float rmax;               // halo radius at which every lane is settled by construction
     int core_e;               // lanes farther than this many cells from the leader wait for their own pass
     int warp_bytes;           // shared-memory stride between the stage buffers of two warps
@@ -165,12 +166,29 @@ __device__ __forceinline__ void tile_search_row(const LinParams& P, const TilePa
             const uint32_t total = mode == 1 ? total_any : 0u;
             const uint32_t all = __reduce_add_sync(FULL, gl == 0 ? total : 0u);
             if (all > 0u) {
-                // ---- stage: one bulk copy per non-empty row, then every lane scans EVERY candidate its group staged ----
-                if (lane == 0) mbar_expect_tx(bar, all * 32u);
-                __syncwarp();
-                if (mode == 1 && gl < nfit && lenp) bulk_g2s(gpts + 2 * (incl - lenp), G.pairs + 2 * (size_t)ps, lenp * 32u, bar);
-                mbar_wait(bar, phase);
-                phase ^= 1u;
+                // ---- stage: every non-empty row range -> the group's slice, then every lane scans EVERY candidate its
+                //      group staged.  A range of at least bulk_min pair records is ONE bulk copy (TMA engine, completion
+                //      on the mbarrier); shorter ones are copied by their lane with 16-byte loads: the TMA engine needs
+                //      ~50 ns per copy whatever its size (measured, profiles/r2_notes.md), which bounds a kernel that
+                //      issues a dozen 100-byte copies per row ----
+                const bool mine = mode == 1 && gl < nfit && lenp > 0u;
+                const bool bulk = mine && lenp >= (uint32_t)TP.bulk_min;
+                const uint32_t bulk_pairs = __reduce_add_sync(FULL, bulk ? lenp : 0u);
+                if (bulk_pairs) {
+                    if (lane == 0) mbar_expect_tx(bar, bulk_pairs * 32u);
+                    __syncwarp();
+                    if (bulk) bulk_g2s(gpts + 2 * (incl - lenp), G.pairs + 2 * (size_t)ps, lenp * 32u, bar);
+                }
+                if (mine && !bulk) {
+                    const float4* src = G.pairs + 2 * (size_t)ps;
+                    float4* dst = gpts + 2 * (incl - lenp);
+                    for (uint32_t k = 0; k < 2u * lenp; ++k) dst[k] = __ldg(src + k);
+                }
+                if (bulk_pairs) {
+                    mbar_wait(bar, phase);
+                    phase ^= 1u;
+                }
+                __syncwarp();                                    // lane-copied ranges are visible to the whole warp
                 float best = b.d2;
                 const uint32_t trip = tile_scan_pairs(gpts, total, q, best);
                 if (trip != kTileNone) tile_take(gpts, trip, total, q, best, b);
@@ -195,7 +213,7 @@ __device__ __forceinline__ void tile_search_row(const LinParams& P, const TilePa
         }
         todo &= ~__ballot_sync(FULL, settled);
     }
-    smatch[lane] = make_float4(b.x, b.y, b.z, __uint_as_float(b.pos));
+    if (smatch) smatch[lane] = make_float4(b.x, b.y, b.z, __uint_as_float(b.pos));
     if (TP.match_out) TP.match_out[i] = b.pos != kTileNone ? (int)TP.perm[b.pos] : -1;
     // first guess of the next linearisation: a little more than the farthest correspondence of this row
     float need = b.pos != kTileNone ? sqrtf(b.d2) * G.inv_c : 0.0f;
@@ -274,6 +292,38 @@ __global__ void __launch_bounds__(kLinThreads, MINB) tile_linearize_kernel(const
     if (lane < NACC) sh.red[warp][lane] = acc64;
     __syncthreads();
     block_finish<METHOD>(P, sh);
+}
+
+// Split form: correspondences only (the matched position in the SOURCE index is parked per scan
+// slot, TP.match_out), followed by accumulate_kernel.  No accumulators and no method dependence: the
+// kernel keeps few registers, so twice as many warps are resident to hide the latency chain of a row
+// (scan load -> cell starts -> bulk copy -> scan), which is what bounds the fused form.
+template <int MINB, int NG>
+__global__ void __launch_bounds__(kLinThreads, MINB) tile_correspond_kernel(const LinParams P, const TileParams TP) {
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    __shared__ BlockShared sh;
+    __shared__ Pose32 spose;
+    constexpr int NWARP = kLinThreads / 32;
+    {
+        Pose32 pose;
+        if (!load_pose(P, sh, pose)) return;
+        if (threadIdx.x == 0) spose = pose;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wbase = tile_smem + (size_t)warp * TP.warp_bytes;
+    float4* spts = reinterpret_cast<float4*>(wbase);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(wbase + (size_t)TP.cap * 16);
+    if (lane == 0) {
+        mbar_init(bar, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    uint32_t phase = 0u;
+    const long long rows = P.n_pad >> 5;
+    const long long nwarps = (long long)gridDim.x * NWARP;
+    for (long long row = (long long)blockIdx.x * NWARP + warp; row < rows; row += nwarps)
+        tile_search_row<NG>(P, TP, &spose, row, lane, spts, bar, phase, nullptr);
 }
 
 }  // namespace pcr

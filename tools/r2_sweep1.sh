@@ -16,15 +16,13 @@ except Exception as e:
     print(n, "failed", e, flush=True)
 PY
 }
-run c2_default c2 A=1
-run c2_g1 c2 PCR_TILE_G=1
-run c2_g2 c2 PCR_TILE_G=2
-run c2_g8 c2 PCR_TILE_G=8
-run c2_g4_ppc4 c2 PCR_TILE_PPC=4
-run c2_g8_ppc4 c2 PCR_TILE_G=8 PCR_TILE_PPC=4
-run c2_g8_ppc2 c2 PCR_TILE_G=8 PCR_TILE_PPC=2 PCR_TILE_CORE=16
-run c2_g4_minb4 c2 PCR_TILE_MINB=4
-run c3_default c3 A=1
-run c3_g8 c3 PCR_TILE_G=8
-run c4_default c4 A=1
-run c4_g8 c4 PCR_TILE_G=8
+run c2_fused_bulk1 c2 PCR_TILE_BULK_MIN=1
+run c2_fused_bulk9 c2 PCR_TILE_BULK_MIN=9
+run c2_fused_bulk33 c2 PCR_TILE_BULK_MIN=33
+run c2_fused_bulk9_g4 c2 PCR_TILE_BULK_MIN=9 PCR_TILE_G=4
+run c2_split5_bulk9 c2 PCR_TILE_SPLIT=1
+run c2_split5_bulk9_g4 c2 PCR_TILE_SPLIT=1 PCR_TILE_G=4
+run c2_fused_bulk9_ppc4 c2 PCR_TILE_PPC=4
+run c3_fused_bulk9 c3 A=1
+run c3_split5_bulk9 c3 PCR_TILE_SPLIT=1
+run c4_fused_bulk9 c4 A=1
