@@ -779,14 +779,10 @@ static int build_voxel_lists(pcr_ctx* ctx) {
 // ---------------------------------------------------------------------------------------
 // per-cell shell lists over the target-point grid (see ShellLists in pcr_common.cuh)
 // ---------------------------------------------------------------------------------------
-// level j >= 1 holds margins in (frac[j-1], frac[j]] cell edges (cut at dmax), frac growing by
-// 2^(1/4) per level up to 2 cell edges; level 0 = the cell's own points
-__constant__ float kShellFrac[PCR_SHELL_LEVELS] = {
-    0.0f, 0.0442f, 0.0526f, 0.0625f, 0.0743f, 0.0884f, 0.1051f, 0.125f, 0.1487f, 0.1768f, 0.2102f, 0.25f,
-    0.2973f, 0.3536f, 0.4204f, 0.5f, 0.5946f, 0.7071f, 0.8409f, 1.0f, 1.1892f, 1.4142f, 1.6818f, 2.0f};
+__constant__ float kShellFrac[PCR_SHELL_LEVELS] = {PCR_SHELL_FRACS};   // level margins in cell edges, see pcr_common.cuh
 
-// One thread per (brick, bit) of the band.  FILL = false: counts[ordinal] = list length padded to
-// a multiple of four; FILL = true: write the entries level by level, the sentinels and the
+// One thread per (brick, bit) of the band.  FILL = false: counts[ordinal] = list length in GROUPS of
+// four entries; FILL = true: write the entries level by level, the sentinels and the
 // per-group margin bounds.  dmax <= R cell edges, so the (2R+1)^3 block holds every point within dmax.
 template <bool FILL>
 __global__ void shell_build_kernel(GridView G, const BrickRec* __restrict__ band, unsigned long long nbricks, float dmax, int R,
@@ -811,7 +807,7 @@ __global__ void shell_build_kernel(GridView G, const BrickRec* __restrict__ band
     uint32_t cnt[PCR_SHELL_LEVELS];
 #pragma unroll
     for (int l = 0; l < PCR_SHELL_LEVELS; ++l) cnt[l] = 0u;
-    uint32_t base = FILL ? start[ord] : 0u;
+    const size_t base = FILL ? 4 * (size_t)start[ord] : 0;      // list offsets count groups of four entries
     for (int pass = 0; pass < (FILL ? 2 : 1); ++pass) {
         long long cached = -1;
         uint4 rec = make_uint4(0, 0, 0, 0);
@@ -858,7 +854,7 @@ __global__ void shell_build_kernel(GridView G, const BrickRec* __restrict__ band
 #pragma unroll
             for (int l = 0; l < PCR_SHELL_LEVELS; ++l) total += cnt[l];
             const uint32_t padded = (total + 3u) & ~3u;
-            if (!FILL) { counts[ord] = padded; return; }
+            if (!FILL) { counts[ord] = padded >> 2; return; }
             // per-group lower bound of the squared margin (slack covers the query's binning error),
             // then turn the level counts into write cursors for the second pass
             const float slack_w = G.slack * G.h;
@@ -903,11 +899,11 @@ static int build_shell_lists(pcr_ctx* ctx) {
     BrickRec* lb = ctx->shell_bricks.as<BrickRec>();
     const long long nthreads = (long long)nbricks * 64;
     // the requested margin first, then smaller ones until the lists fit the memory cap
-    const double tries[4] = {ctx->shell_dmax_frac, 1.5, 1.0, 0.5};
-    for (int t = 0; t < 4; ++t) {
+    const double tries[5] = {ctx->shell_dmax_frac, 2.0, 1.5, 1.0, 0.5};
+    for (int t = 0; t < 5; ++t) {
         const double frac = tries[t];
         if (t > 0 && frac >= tries[0]) continue;
-        const int R = frac <= 1.0 ? 1 : 2;                   // build neighbourhood and band dilation (cells)
+        const int R = frac <= 1.0 ? 1 : (frac <= 2.0 ? 2 : 3);   // build neighbourhood and band dilation (cells)
         const float dmax = (float)(frac * (double)G.h);
         PCR_CUDA(cudaMemsetAsync(lb, 0, (size_t)nbricks * sizeof(BrickRec), ctx->stream));
         band_mark_kernel<<<blocks_for(G.n_pts, 128), 128, 0, ctx->stream>>>(G, lb, R);
@@ -940,16 +936,19 @@ static int build_shell_lists(pcr_ctx* ctx) {
         PCR_CUDA(ctx->cub_tmp.ensure(tmp));
         PCR_CUDA(cub::DeviceReduce::Sum(ctx->cub_tmp.p, tmp, counts64, d_total, (long long)n_band, ctx->stream));
         ctx->launches += 1;
-        unsigned long long total = 0;
-        PCR_CUDA(cudaMemcpyAsync(&total, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        unsigned long long total_groups = 0;
+        PCR_CUDA(cudaMemcpyAsync(&total_groups, d_total, 8, cudaMemcpyDeviceToHost, ctx->stream));
         PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+        const unsigned long long total = 4ull * total_groups;                         // entries
         const double gib = (double)total * 17.0 / (1024.0 * 1024.0 * 1024.0);
-        if (total >= (1ull << 32) - 8ull || gib > ctx->shell_max_gib) continue;      // too large: try a smaller margin
+        // the margin of three cells (2.5x the memory of two) is for targets whose lists stay small
+        const double cap_gib = frac > 2.0 ? std::min(ctx->shell_max_gib, ctx->shell_wide_gib) : ctx->shell_max_gib;
+        if (total_groups >= (1ull << 32) - 8ull || gib > cap_gib) continue;           // too large: try a smaller margin
         rc = exclusive_sum_u32(ctx, counts, ctx->shell_start.as<uint32_t>(), (long long)n_band + 1);
         if (rc) return rc;
-        const uint32_t n_entries = (uint32_t)total;
+        const unsigned long long n_entries = total;
         PCR_CUDA(ctx->shell_pts.ensure(((size_t)n_entries + 4) * sizeof(float4)));
-        PCR_CUDA(ctx->shell_margin2.ensure(((size_t)n_entries / 4 + 1) * 4));
+        PCR_CUDA(ctx->shell_margin2.ensure(((size_t)total_groups + 1) * 4));
         pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(ctx->shell_pts.as<float4>(), (long long)n_entries, nullptr, 0);
         PCR_LAUNCH_CHECK();
         shell_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, dmax, R, nullptr, ctx->shell_start.as<uint32_t>(),
@@ -964,7 +963,7 @@ static int build_shell_lists(pcr_ctx* ctx) {
         ctx->tgt_shell.covered2 = cov * cov;
         ctx->tgt_shell.block_r = (double)dmax >= 1.7320508 * (double)G.h * 1.0001 ? 1 : 0;
         ctx->n_shell_band = n_band;
-        ctx->n_shell_entries = n_entries;
+        ctx->n_shell_entries = (long long)n_entries;
         ctx->shell_dmax_used = frac;
         return PCR_OK;
     }
@@ -1380,8 +1379,9 @@ int pcr_create(int device_id, pcr_ctx** out) {
     }
     if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) >= 3 && atoi(e) <= 6 ? atoi(e) : 0;
     if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 24.0;
-    if (const char* e = getenv("PCR_SHELL_DMAX")) ctx->shell_dmax_frac = atof(e) > 0.0 && atof(e) <= 2.0 ? atof(e) : 1.0;
-    if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 24.0;
+    if (const char* e = getenv("PCR_SHELL_DMAX")) ctx->shell_dmax_frac = atof(e) > 0.0 && atof(e) <= PCR_SHELL_MAX_MARGIN ? atof(e) : 1.0;
+    if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 96.0;
+    if (const char* e = getenv("PCR_SHELL_WIDE_GIB")) ctx->shell_wide_gib = atof(e) >= 0.0 ? atof(e) : 8.0;
     if (const char* e = getenv("PCR_LIST_DILATE")) ctx->list_dilate = atoi(e) >= 1 && atoi(e) <= 4 ? atoi(e) : 3;
     if (const char* e = getenv("PCR_LIST_RADIUS")) ctx->list_radius = atoi(e) >= 2 && atoi(e) <= 6 ? atoi(e) : 5;
     if (const char* e = getenv("PCR_BALL_FIRST")) ctx->ball_first = atoi(e) != 0;

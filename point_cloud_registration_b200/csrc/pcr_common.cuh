@@ -177,11 +177,17 @@ struct CandLists {
 // instruction, the rest waiting for stragglers).  If the list ends while the best is still
 // farther than dmax, the general search takes over from that bound.
 #define PCR_SHELL_LEVELS 24
+// level j >= 1 holds margins in (frac[j-1], frac[j]] cell edges (cut at dmax), frac growing by a
+// constant factor (1.2113) per level up to 3 cell edges; level 0 = the cell's own points
+#define PCR_SHELL_FRACS                                                                                                     \
+    0.0f, 0.0442f, 0.0535f, 0.0649f, 0.0786f, 0.0952f, 0.1153f, 0.1396f, 0.1691f, 0.2049f, 0.2482f, 0.3006f, 0.3641f, 0.4411f, \
+        0.5343f, 0.6472f, 0.7839f, 0.9496f, 1.1502f, 1.3933f, 1.6877f, 2.0443f, 2.4763f, 3.0f
+#define PCR_SHELL_MAX_MARGIN 3.0
 struct ShellLists {
     const uint4* bricks;         // (band mask lo, hi, ordinal of first band cell, unused), brick layout of the grid
-    const uint32_t* start;       // [n_band + 1], multiples of 4
-    const float4* pts;           // entries (+ 4 sentinels)
-    const float* margin2;        // [entries / 4]
+    const uint32_t* start;       // [n_band + 1], in GROUPS of four entries (2^32 groups = 2^34 entries: a 100M-point target fits)
+    const float4* pts;           // entries (+ 4 sentinels): group g = pts[4g .. 4g+3]
+    const float* margin2;        // [groups]
     float covered2;              // (dmax - slack)^2: a best within it after the whole list is final
     int block_r;                 // the lists hold EVERY point of the (2 block_r + 1)^3 cell block around their cell
                                  // (1 when dmax >= sqrt(3) cell edges, else 0: only the cell itself)

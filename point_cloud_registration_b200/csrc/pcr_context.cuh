@@ -96,8 +96,9 @@ struct pcr_ctx {
     long long n_shell_band = 0, n_shell_entries = 0;
     bool shell_tried = false;     // pcr_build_correspondence_lists ran for the current grid
     int use_shell_lists = 1;
-    double shell_dmax_frac = 2.0; // requested list margin in cell edges (<= 2); reduced until the lists fit shell_max_gib
-    double shell_max_gib = 24.0;  // memory cap of the lists
+    double shell_dmax_frac = 3.0; // requested list margin in cell edges (<= 3); reduced until the lists fit the caps below
+    double shell_max_gib = 96.0;  // memory cap of the lists (a B200 has 180 GB; 100M target points at margin 1.5 need 76 GB)
+    double shell_wide_gib = 8.0;  // ... and of lists with a margin above two cells (worth their 2.5x memory for small targets only)
     double shell_dmax_used = 0.0; // margin actually built (0: no lists)
 
     // ---- voxel statistics (VPlaneICP / NDT / VoxelGrid facade) ----

@@ -270,7 +270,7 @@ PCR_HD int grid_nn(const GridView& G, float qx, float qy, float qz, float max_d2
 // Four squared distances of one structure-of-arrays group (see ShellLists) to the query, in packed
 // f32x2 arithmetic on sm_100 (same roundings as dist2_rn); updates the best and its list offset.
 PCR_HD void shell_eval_group(const float4& X, const float4& Y, const float4& Z, float qx, float qy, float qz, uint32_t k,
-                             float& best, uint32_t& best_k) {
+                             float& best, uint32_t& best_k, uint32_t& best_j) {
     float d0, d1, d2, d3;
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 1000
     const float2 nx = make_float2(-qx, -qx), ny = make_float2(-qy, -qy), nz = make_float2(-qz, -qz);
@@ -287,24 +287,26 @@ PCR_HD void shell_eval_group(const float4& X, const float4& Y, const float4& Z, 
     const float dm = fminf(fminf(d0, d1), fminf(d2, d3));
     if (dm < best) {                                          // rare after the first groups
         best = dm;
-        best_k = k + (dm == d0 ? 0u : (dm == d1 ? 1u : (dm == d2 ? 2u : 3u)));
+        best_k = k;
+        best_j = dm == d0 ? 0u : (dm == d1 ? 1u : (dm == d2 ? 2u : 3u));
     }
 }
 
 // Cursor over the shell list (see ShellLists) of one query's cell.
 struct ShellCursor {
-    uint32_t k;                // list offset of the next group (entries; multiple of 4)
+    uint32_t k;                // next group of the list (offsets count GROUPS of four entries)
     uint32_t e;                // end of the list
     float m;                   // margin bound of the next group (already loaded)
     float best;                // best squared distance so far (starts at max_dist^2, strict <)
-    uint32_t best_k;           // list offset of the best entry, 0xffffffff = none
+    uint32_t best_k;           // group of the best entry, 0xffffffff = none
+    uint32_t best_j;           // ... and its place (0..3) in that group
     bool active;               // more groups to evaluate
     bool exhausted;            // the list ended (or will end) without a margin bound stopping the scan
 };
 
 // Open the list of the query's cell.  false: the cell has no list (nothing was looked at).
 PCR_HD bool shell_open(const GridView& G, const ShellLists& S, float qx, float qy, float qz, float max_d2, ShellCursor& c) {
-    c.active = false; c.exhausted = true; c.best = max_d2; c.best_k = 0xffffffffu;
+    c.active = false; c.exhausted = true; c.best = max_d2; c.best_k = 0xffffffffu; c.best_j = 0u;
     const float gx = (qx - G.ox) * G.inv_h, gy = (qy - G.oy) * G.inv_h, gz = (qz - G.oz) * G.inv_h;
     if (!(gx >= 0.0f && gy >= 0.0f && gz >= 0.0f && gx < (float)G.cnx && gy < (float)G.cny && gz < (float)G.cnz)) return false;
     const int cx = (int)gx, cy = (int)gy, cz = (int)gz;
@@ -315,7 +317,7 @@ PCR_HD bool shell_open(const GridView& G, const ShellLists& S, float qx, float q
     const uint32_t ord = rec.z + (uint32_t)popc64(band & ((1ull << bit) - 1ull));
     const uint32_t s = S.start[ord], e = S.start[ord + 1];
     c.k = s; c.e = e;
-    c.m = S.margin2[s >> 2];                                  // (one bound past the end of the array is allocated)
+    c.m = S.margin2[s];                                       // (one bound past the end of the array is allocated)
     if (s < e) {
         if (c.m >= c.best) c.exhausted = false;               // not even the first group can hold a match
         else c.active = true;
@@ -325,7 +327,7 @@ PCR_HD bool shell_open(const GridView& G, const ShellLists& S, float qx, float q
 
 // Advance an active cursor past the group just evaluated; termination tests.
 PCR_HD void shell_advance(ShellCursor& c, float m_next) {
-    c.k += 4; c.m = m_next;
+    c.k += 1; c.m = m_next;
     if (!(c.k < c.e)) c.active = false;                       // list ended
     else if (c.m >= c.best) { c.active = false; c.exhausted = false; }   // everything from here on is at least this far
 }
@@ -337,8 +339,8 @@ PCR_HD int shell_close(const ShellLists& S, const ShellCursor& c, float& out_d2,
     out_d2 = c.best;
     out_pos = -1;
     if (c.best_k != 0xffffffffu) {
-        const float4 W = S.pts[(c.best_k & ~3u) + 3u];
-        const uint32_t j = c.best_k & 3u;
+        const float4 W = S.pts[4 * (size_t)c.best_k + 3];
+        const uint32_t j = c.best_j;
         const float w = j == 0u ? W.x : (j == 1u ? W.y : (j == 2u ? W.z : W.w));
 #if defined(__CUDA_ARCH__)
         out_pos = __float_as_int(w);
@@ -354,10 +356,10 @@ PCR_HD int shell_scan(const GridView& G, const ShellLists& S, float qx, float qy
     ShellCursor c;
     if (!shell_open(G, S, qx, qy, qz, max_d2, c)) return 0;
     while (c.active) {
-        const float4* g4 = S.pts + c.k;
+        const float4* g4 = S.pts + 4 * (size_t)c.k;
         const float4 X = g4[0], Y = g4[1], Z = g4[2];
-        const float mn = S.margin2[(c.k >> 2) + 1];
-        shell_eval_group(X, Y, Z, qx, qy, qz, c.k, c.best, c.best_k);
+        const float mn = S.margin2[c.k + 1];
+        shell_eval_group(X, Y, Z, qx, qy, qz, c.k, c.best, c.best_k, c.best_j);
         shell_advance(c, mn);
     }
     return shell_close(S, c, out_d2, out_pos);

@@ -284,9 +284,11 @@ __device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32
             for (int r = r0; r < r1; ++r) correspond_slot<METHOD>(P, pose, ((long long)r << 5) + lane, lists);
         }
     } else {
+        // static partition of the fused form: the SAME quads of slots the thread accumulates afterwards
+        // (accumulate_pass reads the positions parked here without any grid-wide synchronisation)
         const long long stride = (long long)gridDim.x * kLinThreads;
-        for (long long i = blockIdx.x * (long long)kLinThreads + threadIdx.x; i < P.n_pad; i += stride)
-            correspond_slot<METHOD>(P, pose, i, lists);
+        for (long long t = blockIdx.x * (long long)kLinThreads + threadIdx.x; t < (P.n_pad >> 2); t += stride)
+            for (int u = 0; u < 4; ++u) correspond_slot<METHOD>(P, pose, 4 * t + u, lists);
     }
 }
 

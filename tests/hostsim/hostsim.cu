@@ -139,15 +139,8 @@ void hs_knn(void* gp, const float* q, int64_t m, int k, int64_t* idx, float* dis
 int64_t hs_shell_build(void* gp, double dmax_frac) {
     HostGrid* g = (HostGrid*)gp;
     const GridView& G = g->v;
-    static const signed char order[27][3] = {
-        {0, 0, 0},
-        {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}, {0, 0, -1}, {0, 0, 1},
-        {-1, -1, 0}, {1, -1, 0}, {-1, 1, 0}, {1, 1, 0}, {-1, 0, -1}, {1, 0, -1}, {-1, 0, 1}, {1, 0, 1}, {0, -1, -1}, {0, 1, -1}, {0, -1, 1}, {0, 1, 1},
-        {-1, -1, -1}, {1, -1, -1}, {-1, 1, -1}, {1, 1, -1}, {-1, -1, 1}, {1, -1, 1}, {-1, 1, 1}, {1, 1, 1}};
-    static const float frac[PCR_SHELL_LEVELS] = {
-        0.0f, 0.0442f, 0.0526f, 0.0625f, 0.0743f, 0.0884f, 0.1051f, 0.125f, 0.1487f, 0.1768f, 0.2102f, 0.25f,
-        0.2973f, 0.3536f, 0.4204f, 0.5f, 0.5946f, 0.7071f, 0.8409f, 1.0f, 1.1892f, 1.4142f, 1.6818f, 2.0f};
-    const int R = dmax_frac <= 1.0 ? 1 : 2;
+    static const float frac[PCR_SHELL_LEVELS] = {PCR_SHELL_FRACS};
+    const int R = dmax_frac <= 1.0 ? 1 : (dmax_frac <= 2.0 ? 2 : 3);
     const int side = 2 * R + 1, ncell = side * side * side, centre = (ncell - 1) / 2;
     const float dmax = (float)(dmax_frac * (double)G.h);
     const size_t nb = (size_t)G.bnx * G.bny * G.bnz;
@@ -203,8 +196,7 @@ int64_t hs_shell_build(void* gp, double dmax_frac) {
                     lv[lvl].push_back(make_float4(t.x, t.y, t.z, w));
                 }
             }
-            const uint32_t base = (uint32_t)g->shell_pts.size();
-            g->shell_start.push_back(base);
+            g->shell_start.push_back((uint32_t)(g->shell_pts.size() / 4));      // offsets count groups of four entries
             std::vector<float4> flat;
             std::vector<float> bounds;
             for (int l = 0; l < PCR_SHELL_LEVELS; ++l) {
@@ -227,7 +219,7 @@ int64_t hs_shell_build(void* gp, double dmax_frac) {
             ++ord;
         }
     }
-    g->shell_start.push_back((uint32_t)g->shell_pts.size());
+    g->shell_start.push_back((uint32_t)(g->shell_pts.size() / 4));
     const int64_t n_entries = (int64_t)g->shell_pts.size();
     for (int k = 0; k < 4; ++k) g->shell_pts.push_back(make_float4(3.0e38f, 3.0e38f, 3.0e38f, 0.f));
     g->shell_margin2.push_back(3.0e38f);
@@ -256,9 +248,9 @@ void hs_shell_nn(void* gp, const float* q, int64_t m, double max_dist, int64_t* 
             int st = 0;
             if (ok) {
                 while (c.active) {
-                    const float4* g4 = g->shell.pts + c.k;
-                    shell_eval_group(g4[0], g4[1], g4[2], q[3 * i], q[3 * i + 1], q[3 * i + 2], c.k, c.best, c.best_k);
-                    shell_advance(c, g->shell.margin2[(c.k >> 2) + 1]);
+                    const float4* g4 = g->shell.pts + 4 * (size_t)c.k;
+                    shell_eval_group(g4[0], g4[1], g4[2], q[3 * i], q[3 * i + 1], q[3 * i + 2], c.k, c.best, c.best_k, c.best_j);
+                    shell_advance(c, g->shell.margin2[c.k + 1]);
                 }
                 st = shell_close(g->shell, c, d2, pos);
             }
@@ -313,11 +305,11 @@ void hs_shell_study(void* gp, const float* q, int64_t m, double max_dist, double
             long long groups = 0;
             uint32_t k = S.start[ord];
             const uint32_t e = S.start[ord + 1];
-            for (; k < e; k += 4) {
-                if (S.margin2[k >> 2] >= best) break;
+            for (; k < e; k += 1) {
+                if (S.margin2[k] >= best) break;
                 ++groups;
                 {
-                    const float4 X = S.pts[k], Y = S.pts[k + 1], Z = S.pts[k + 2];
+                    const float4 X = S.pts[4 * (size_t)k], Y = S.pts[4 * (size_t)k + 1], Z = S.pts[4 * (size_t)k + 2];
                     const float xs[4] = {X.x, X.y, X.z, X.w}, ys[4] = {Y.x, Y.y, Y.z, Y.w}, zs[4] = {Z.x, Z.y, Z.z, Z.w};
                     for (int u = 0; u < 4; ++u) {
                         const float d = dist2_rn(xs[u] - qx, ys[u] - qy, zs[u] - qz);

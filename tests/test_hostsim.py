@@ -133,7 +133,7 @@ def test_nn_degenerate(hs):
     check_nn(hs, big, (rng.random((500, 3)) * 900 - 450).astype(np.float32), 25.0)
 
 
-@pytest.mark.parametrize("dmax_frac", [1.0, 0.5, 1.7, 2.0])
+@pytest.mark.parametrize("dmax_frac", [1.0, 0.5, 1.7, 2.0, 2.6, 3.0])
 def test_shell_lists_match_general_search(hs, dmax_frac):
     """shell_nn (margin-ordered per-cell lists, margin-bound termination, continuation into the
     general search) returns exactly what grid_search() returns, for every regime: on the surface,

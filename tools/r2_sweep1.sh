@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2 sweep 1: tile-stream tunables on C2 (and one C3/C4 line each)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tile_stream or linearize_10k or align_10k" > gpurun_out/r2_s1_tests.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "shell_lists or linearize_10k or align_10k or scheduling" > gpurun_out/r2_s1_tests.log 2>&1
 tail -2 gpurun_out/r2_s1_tests.log
 run() {  # name, workload, env...
   name=$1; wl=$2; shift 2
@@ -16,13 +16,7 @@ except Exception as e:
     print(n, "failed", e, flush=True)
 PY
 }
-run c2_fused_bulk1 c2 PCR_TILE_BULK_MIN=1
-run c2_fused_bulk9 c2 PCR_TILE_BULK_MIN=9
-run c2_fused_bulk33 c2 PCR_TILE_BULK_MIN=33
-run c2_fused_bulk9_g4 c2 PCR_TILE_BULK_MIN=9 PCR_TILE_G=4
-run c2_split5_bulk9 c2 PCR_TILE_SPLIT=1
-run c2_split5_bulk9_g4 c2 PCR_TILE_SPLIT=1 PCR_TILE_G=4
-run c2_fused_bulk9_ppc4 c2 PCR_TILE_PPC=4
-run c3_fused_bulk9 c3 A=1
-run c3_split5_bulk9 c3 PCR_TILE_SPLIT=1
-run c4_fused_bulk9 c4 A=1
+run c2_lists_m3 c2 A=1
+run c2_lists_m2 c2 PCR_SHELL_DMAX=2
+run c2_lists_m3_ppc16 c2 PCR_TARGET_PPC=16
+run c2_lists_m3_ppc32 c2 PCR_TARGET_PPC=32
