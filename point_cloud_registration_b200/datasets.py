@@ -1,10 +1,12 @@
 """Workload generators and a minimal PCD reader (host side, NumPy only).
 
 The reference benchmarks on ``data/B-01.pcd`` through ``benchmark/test_data.py:21-44``
-(scan = rigidly moved, noised copy of the map).  That file cannot travel to the GPU box,
-so the bench/test workloads are synthetic scenes with the same character (SURVEY.md
-section 8d): 2-D surfaces embedded in 3-D at B-01's surface density (~170 pts/m^2) so that
-kNN normals and voxel planes are meaningful and occupied 0.5 m voxels hold >= 10 points.
+(scan = rigidly moved, noised copy of the map).  The xyz columns of that file travel with this
+repository as ``data/b01_xyz.npz`` (CC BY 4.0, see data/README.md; made by tools/make_b01_npz.py)
+and are what the C2 benchmark runs on; the 10M / 100M configurations are synthetic scenes with the
+same character: 2-D surfaces embedded in 3-D at B-01's surface density
+(~170 pts/m^2) so that kNN normals and voxel planes are meaningful and occupied 0.5 m voxels hold
+>= 10 points.
 """
 from __future__ import annotations
 
@@ -87,6 +89,65 @@ def make_urban_slab(n_points, seed=0, density=SURFACE_DENSITY, dtype=np.float32)
     out += rng.normal(0.0, 0.01, out.shape)              # surface roughness
     rng.shuffle(out, axis=0)                             # acquisition order is not spatial
     return out.astype(dtype)
+
+
+import os
+
+B01_NPZ = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "b01_xyz.npz")
+C2_LEVER_ARM = 42.0      # metres: corner radius of the 1.19M-point slab (and ~ the half diagonal of B-01's busy part)
+
+
+def load_b01():
+    """(1193011, 3) float32 xyz of the reference's data/B-01.pcd from data/b01_xyz.npz, or None if
+    the file is not there (callers then fall back to a synthetic slab of the same size and say so)."""
+    if not os.path.exists(B01_NPZ):
+        return None
+    with np.load(B01_NPZ) as z:
+        return np.ascontiguousarray(z["xyz"], dtype=np.float32)
+
+
+def reference_keys(points, voxel_size):
+    """The reference's lossy voxel hash (voxel.py:12-21, quirk Q9) -- same arithmetic as
+    point_cloud_registration_b200.voxel.get_keys, repeated here so that the generators do not import
+    the GPU package."""
+    c = np.floor(np.asarray(points) / voxel_size).astype(np.int64)
+    p, m = 116101, 10000000000
+    return ((c[:, 2] * p % m + c[:, 1]) * p) % m + c[:, 0]
+
+
+def assert_no_key_collisions(points, voxel_sizes=(0.5, 1.0)):
+    """the reference groups points by a LOSSY hash of the voxel coordinate, this
+    library by the exact coordinate.  The two partitions agree iff no two distinct voxels share a hash
+    key -- assert it for every workload the two are compared on.  Works for NumPy arrays and torch
+    tensors (the 100M-point clouds live on the GPU)."""
+    for vs in voxel_sizes:
+        if hasattr(points, "detach"):                      # torch tensor
+            import torch
+            c = torch.floor(points.to(torch.float32) / np.float32(vs)).to(torch.int64)
+            p, m = 116101, 10000000000
+            key = torch.remainder(torch.remainder(c[:, 2] * p, m) + c[:, 1], m)      # Python floor-mod semantics
+            key = torch.remainder(key * p, m) + c[:, 0]
+            lo = c.min(dim=0).values
+            ext = (c.max(dim=0).values - lo + 1)
+            exact = ((c[:, 2] - lo[2]) * ext[1] + (c[:, 1] - lo[1])) * ext[0] + (c[:, 0] - lo[0])
+            n_key, n_exact = int(torch.unique(key).numel()), int(torch.unique(exact).numel())
+        else:
+            pts = np.asarray(points)
+            c = np.floor(pts / pts.dtype.type(vs)).astype(np.int64)
+            key = reference_keys(pts, pts.dtype.type(vs))
+            lo = c.min(axis=0)
+            ext = c.max(axis=0) - lo + 1
+            exact = ((c[:, 2] - lo[2]) * ext[1] + (c[:, 1] - lo[1])) * ext[0] + (c[:, 0] - lo[0])
+            n_key, n_exact = len(np.unique(key)), len(np.unique(exact))
+        assert n_key == n_exact, (f"voxel size {vs}: the reference's get_keys hash merges {n_exact - n_key} voxels "
+                                  "(quirk Q9): this cloud cannot be used to compare the two voxel partitions")
+
+
+def lever_arm_so3(so3, points_radius, ref_radius=C2_LEVER_ARM):
+    """Rotation vector scaled so that the scene's rim moves as far as C2's does: a fixed 0.037 rad
+    displaces the corner of a 540 m slab by 14 m -- far beyond max_dist, where no ICP (the reference
+    included) converges.  Scenes no larger than C2 keep the section-8d rotation."""
+    return tuple(float(v) * min(1.0, ref_radius / max(float(points_radius), 1e-9)) for v in so3)
 
 
 def perturb_scan(target, so3=(0.01, -0.02, 0.03), t=(0.1, -0.2, 0.3), sigma=0.005, seed=0,

@@ -23,7 +23,8 @@ def test_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "ICP iterations/sec" and d["unit"] == "iterations/s"
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["higher_is_better"] is True
-    assert d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6 * 1e3
+    assert d["value"] > 0 and d["extrapolated"] is False and abs(d["ms_per_step"] * d["value"] - 1e3) < 1e-6 * 1e3
+    assert d["measured"]["scan_points"] == d["config"]["scan_points_measured"] == 30000
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("c2") and d["vs_baseline"] is None
@@ -34,4 +35,7 @@ def test_reference_arm_under_torchrun_only_rank0_prints():
     assert out.strip() == ""
     out = run_reference({"WORLD_SIZE": "2", "RANK": "0", "LOCAL_RANK": "0"}, "--gpus", "2", "--steps", "3", "--warmup", "3")
     d = json.loads(out.strip())
-    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["config"]["workload"].startswith("c5")
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["workload"].startswith("c5")
+    # a bounded sample is labelled as such: ms_per_step is the MEASURED sample time, value the extrapolation
+    assert d["extrapolated"] == (d["measured"]["scan_points"] < d["config"]["scan_points"] or d["measured"]["target_points"] < d["config"]["target_points"])
+    assert abs(d["ms_per_step"] - d["measured"]["ms_per_step"]) < 1e-9
