@@ -237,7 +237,7 @@ def run_reference(args, wl_name, wl, world, rank):
     cal = scan_all[rng.choice(len(scan_all), size=min(50_000, len(scan_all)), replace=False)].astype(np.float32)
     time_oracle_steps(o, cal, [np.eye(4)], 1, 1)
     per_point = time_oracle_steps(o, cal, [np.eye(4)], 2, 0) / len(cal)
-    budget_s = float(os.environ.get("REF_BUDGET_S", "100"))
+    budget_s = float(os.environ.get("REF_BUDGET_S", "200"))
     n_s = int(budget_s / (per_point * (args.steps + args.warmup)))
     n_s = max(min(20_000, len(scan_all)), min(n_s, 1_000_000 if bounded else n_total, len(scan_all)))
     log(f"reference arm: {wl['cls']} target {n_t} pts, scan sample {n_s} pts ({per_point * 1e9:.0f} ns/pt calibrated), {cores} host threads")
@@ -345,8 +345,9 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, context_only
         radius = float(torch.linalg.norm(0.5 * ext_xy))
         so3 = ds.lever_arm_so3((0.01, -0.02, 0.03), radius)
         scan_full = ds.perturb_scan_torch(target_in, so3=so3, seed=wl["scan_seed"])
-        data_note = ("synthetic (urban slab at B-01's surface density, generated on the GPU; the CPU legs use the NumPy generator of "
-                     "the same scene family)")
+        scan_full = scan_full[ds.morton_order_torch(scan_full)].contiguous()     # contiguous index ranges = spatial tiles
+        data_note = ("synthetic (urban slab at B-01's surface density, generated on the GPU, scan in Morton order so that every rank's "
+                     "contiguous shard is a spatial tile; the CPU legs use the NumPy generator of the same scene family)")
         torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
     lo, hi = shard_bounds(n_total, rank, world)
@@ -520,7 +521,8 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, context_only
         barrier()
         # the section-8d rotation NOT matched to the lever arm ("far start"): the rim moves by many metres, beyond
         # max_dist -- the reference does not converge there either; first iterations only, for the record
-        scan_far = ds.perturb_scan_torch(target_in, seed=wl["scan_seed"])[lo:hi]
+        scan_far = ds.perturb_scan_torch(target_in, seed=wl["scan_seed"])
+        scan_far = scan_far[ds.morton_order_torch(scan_far)][lo:hi]
         reg.upload_scan(scan_far.contiguous(), sort=True)
         f_ms, _, _ = timed_trajectory(torch, ctx, method, T0, 5, 5, 5, ext, flush, barrier)
         f_local = float(f_ms.sum())

@@ -84,8 +84,8 @@ __device__ __forceinline__ void fetch_match(const LinParams& P, int pos, MatchRe
 }
 
 // ... and this correspondence's terms
-template <int METHOD>
-__device__ __forceinline__ void accumulate_match(const Pose32& pose, float* acc, const MatchRec& r, float px, float py, float pz) {
+template <int METHOD, typename A>
+__device__ __forceinline__ void accumulate_match(const Pose32& pose, A* acc, const MatchRec& r, float px, float py, float pz) {
     float qx, qy, qz;
     transform32(pose, px, py, pz, qx, qy, qz);
     if (METHOD == PCR_METHOD_ICP) {
@@ -189,8 +189,8 @@ __device__ __forceinline__ void block_finish(const LinParams& P, BlockShared& sh
     }
 }
 
-template <int METHOD>
-__device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShared& sh, const float* acc) {
+template <int METHOD, typename A>
+__device__ __forceinline__ void reduce_and_finish(const LinParams& P, BlockShared& sh, const A* acc) {
     constexpr int NRED = NAcc<METHOD>::value;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -303,9 +303,12 @@ __device__ __forceinline__ void accumulate_pass(const LinParams& P, BlockShared&
     constexpr int NACC = NAcc<METHOD>::value;
     const long long quads = P.n_pad >> 2;                        // n_pad is a multiple of 32
     const long long stride = (long long)gridDim.x * kLinThreads;
-    float acc[NACC];
+    // float64 accumulators: per-point terms are float32 products (as the reference's float32 geometry), every
+    // SUM is float64 -- the reference sums in float64 after the gather (ndt.py:39-56), and records no longer
+    // depend on how the scan is split over threads or GPUs beyond 1e-13
+    double acc[NACC];
 #pragma unroll
-    for (int i = 0; i < NACC; ++i) acc[i] = 0.f;
+    for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
     const int4* prev4 = reinterpret_cast<const int4*>(P.prev);
     const float4* sx4 = reinterpret_cast<const float4*>(P.sx);
     const float4* sy4 = reinterpret_cast<const float4*>(P.sy);
@@ -313,14 +316,18 @@ __device__ __forceinline__ void accumulate_pass(const LinParams& P, BlockShared&
     for (long long t = blockIdx.x * (long long)kLinThreads + threadIdx.x; t < quads; t += stride) {
         const int4 pq = prev4[t];
         const int pos[4] = {pq.x, pq.y, pq.z, pq.w};
-        MatchRec rec[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) fetch_match<METHOD>(P, pos[u], rec[u]);
         const float4 X = __ldg(sx4 + t), Y = __ldg(sy4 + t), Z = __ldg(sz4 + t);
         const float px[4] = {X.x, X.y, X.z, X.w}, py[4] = {Y.x, Y.y, Y.z, Y.w}, pz[4] = {Z.x, Z.y, Z.z, Z.w};
+        constexpr int B = METHOD == PCR_METHOD_NDT ? 2 : 4;      // records in flight (an NDT record is 12 registers)
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (pos[u] >= 0) accumulate_match<METHOD>(pose, acc, rec[u], px[u], py[u], pz[u]);
+        for (int h = 0; h < 4; h += B) {
+            MatchRec rec[B];
+#pragma unroll
+            for (int u = 0; u < B; ++u) fetch_match<METHOD>(P, pos[h + u], rec[u]);
+#pragma unroll
+            for (int u = 0; u < B; ++u)
+                if (pos[h + u] >= 0) accumulate_match<METHOD>(pose, acc, rec[u], px[h + u], py[h + u], pz[h + u]);
+        }
     }
     reduce_and_finish<METHOD>(P, sh, acc);
 }
@@ -639,10 +646,7 @@ template <int METHOD>
 static int launch_accumulate(pcr_ctx* ctx, const LinParams& P) {
     int* cache = ctx->lin_blocks_per_sm[METHOD];
     // quads of slots per thread: the grid only needs a quarter of the threads
-    if (ctx->acc_min_blocks == 3) {
-        const int blocks = blocks_for_kernel(ctx, accumulate_kernel<METHOD, 3>, cache[0], (P.n_pad + 3) / 4);
-        accumulate_kernel<METHOD, 3><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
-    } else {
+    {
         const int blocks = blocks_for_kernel(ctx, accumulate_kernel<METHOD, 2>, cache[1], (P.n_pad + 3) / 4);
         accumulate_kernel<METHOD, 2><<<blocks, kLinThreads, 0, ctx->stream>>>(P);
     }

@@ -292,3 +292,20 @@ def perturb_scan_torch(target, so3=(0.01, -0.02, 0.03), t=(0.1, -0.2, 0.3), sigm
     if sigma > 0:
         scan += torch.randn(scan.shape, generator=g, dtype=torch.float64, device=target.device) * sigma
     return scan.to(torch.float32).contiguous()
+
+
+def morton_order_torch(points, bits=10):
+    """Permutation that orders an (n,3) CUDA tensor along a Morton curve of its own bounding box
+    (2^bits cells per axis).  Multi-GPU runs shard the scan by CONTIGUOUS index ranges: sorted like
+    this, every rank owns a spatial tile and streams only its part of the replicated
+    target structure, instead of a random sample of the whole scene."""
+    import torch
+    lo = points.min(dim=0).values
+    ext = (points.max(dim=0).values - lo).max().clamp_min(1e-9)
+    g = ((points - lo) / ext * (2 ** bits - 1)).to(torch.int64).clamp_(0, 2 ** bits - 1)
+    key = torch.zeros(points.shape[0], dtype=torch.int64, device=points.device)
+    for b in range(bits):
+        for a in range(3):
+            key |= ((g[:, a] >> b) & 1) << (3 * b + a)
+    return torch.argsort(key)
+

@@ -34,7 +34,16 @@ def worker(rank, world, port, name, kw, out_dir):
         T0 = np.eye(4)
         H, g, e2 = reg.calc_H_g_e2(T0, scan)            # full scan in, this rank's tile linearised, records all-reduced
         T = reg.align(scan, init_T=T0)
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), H=H, g=g, e2=e2, T=T, iters=reg.last_iterations)
+        iters = reg.last_iterations
+        # a NEW target on the same object: the communicator must follow it (the scan stays sharded, so a
+        # context without communicator would silently solve on half the scan)
+        target2 = ds.make_urban_slab(180_000, seed=23)
+        scan2 = ds.perturb_scan(target2, seed=24, num_points=120_003)
+        reg.set_target(target2)
+        H2, g2, e22 = reg.calc_H_g_e2(T0, scan2)
+        T2 = reg.align(scan2, init_T=T0)
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), H=H, g=g, e2=e2, T=T, iters=iters, H2=H2, e22=e22, T2=T2,
+                 iters2=reg.last_iterations)
     finally:
         dist.destroy_process_group()
 
@@ -54,9 +63,18 @@ def test_two_gpu_matches_one_gpu(tmp_path, name, kw):
     one.set_target(target)
     H, g, e2 = one.calc_H_g_e2(np.eye(4), scan)
     T = one.align(scan, init_T=np.eye(4))
+    it1 = one.last_iterations
+    target2 = ds.make_urban_slab(180_000, seed=23)
+    scan2 = ds.perturb_scan(target2, seed=24, num_points=120_003)
+    one.set_target(target2)
+    H2, g2, e22 = one.calc_H_g_e2(np.eye(4), scan2)
+    T2 = one.align(scan2, init_T=np.eye(4))
     for r in range(2):
         z = np.load(tmp_path / f"rank{r}.npz")
         assert np.max(np.abs(z["H"] - H)) < 1e-9 * np.max(np.abs(H))
         assert abs(float(z["e2"]) - e2) < 1e-9 * e2
         assert np.linalg.norm(z["T"] - T) < 1e-9
-        assert int(z["iters"]) == one.last_iterations
+        assert int(z["iters"]) == it1
+        assert np.max(np.abs(z["H2"] - H2)) < 1e-9 * np.max(np.abs(H2))
+        assert abs(float(z["e22"]) - e22) < 1e-9 * e22
+        assert np.linalg.norm(z["T2"] - T2) < 1e-9 and int(z["iters2"]) == one.last_iterations
