@@ -63,6 +63,12 @@ const char* pcr_last_error(const pcr_ctx* ctx);
  * (icp.py:17-22, plane_icp.py:19-20). */
 int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n);
 
+/* Append points to the resident target cloud (the old part stays on the GPU); every structure over
+ * the target is void afterwards and is rebuilt by the usual build calls, so the result equals
+ * set_target(concatenate(old, new)).  Backs Registration.update_target, which the reference declares
+ * and leaves unimplemented (registration.py:36-43). */
+int pcr_append_target_points(pcr_ctx* ctx, const float* xyz, int64_t n);
+
 /* Build the exact nearest-neighbour index over the target points.  Replaces
  * `KDTree(target)` (kdtree.py:18-25 -> pykdtree; icp.py:20, plane_icp.py:22). */
 int pcr_build_nn_index(pcr_ctx* ctx);
@@ -87,7 +93,8 @@ int pcr_get_normals(pcr_ctx* ctx, float* normals);
  * over the kept means.  `xyz` is (n,3) float32 (is_f64 = 0) or float64 (is_f64 = 1); the
  * statistics are accumulated in float64 exactly as the reference does for either dtype.
  * Replaces VoxelGrid.set_points (voxel.py:104-165) and calc_icov (voxel.py:69-102) as
- * called from voxelized_plane_icp.py:18-21 and ndt.py:18-22. */
+ * called from voxelized_plane_icp.py:18-21 and ndt.py:18-22.  xyz = NULL, n = 0: use the resident
+ * target points (pcr_set_target_points / pcr_append_target_points; float32). */
 int pcr_build_voxels(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size,
                      int min_points, int with_icov);
 
@@ -172,6 +179,14 @@ int pcr_voxel_filter(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, doubl
  * coordinate floor(p / voxel_size) of voxel v (room for n voxels), n_voxels = their number. */
 int pcr_voxel_labels(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size,
                      int64_t* labels, int32_t* coords, int64_t* n_voxels);
+
+/* Per-correspondence Gauss-Newton rows at transform T for the scalar-residual methods (PCR_PLANE,
+ * PCR_VPLANE): rows is (n_scan, 28) float64, C-contiguous, HOST or DEVICE memory, in the scan's storage
+ * order (upload with sort = 0 to keep the caller's order): [0..20] upper triangle of J^T J, [21..26] J r,
+ * [27] r^2 of every scan point (zeros without correspondence); their column sums are the record of
+ * pcr_linearize.  Equals caratheodory.create_gn_set(J, r).T of the reference (caratheodory.py:118-138),
+ * the input of its exact coreset extraction. */
+int pcr_export_gn_rows(pcr_ctx* ctx, int method, const double T[16], double max_dist, double* rows);
 
 /* ---- multi-GPU (scan tile-sharded, target replicated) ----------- */
 

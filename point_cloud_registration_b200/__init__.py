@@ -14,8 +14,9 @@ from .ndt import NDT
 from .kdtree import KDTree
 from .voxel import VoxelGrid, voxel_filter, color_by_voxel, get_keys
 from .estimate_normals import estimate_normals, get_norm_lines, estimate_norm_with_tree
+from .caratheodory import caratheodory, fast_caratheodory, create_gn_set, gn_set_from_registration
 
 __all__ = ["Registration", "UploadedScan", "ICP", "PlaneICP", "VPlaneICP", "NDT", "KDTree", "VoxelGrid",
            "voxel_filter", "color_by_voxel", "get_keys", "estimate_normals", "estimate_norm_with_tree", "get_norm_lines",
            "makeRt", "makeT", "expSO3", "plus", "skew", "skews", "skew2", "skew_time_vector",
-           "transform_points", "huber_weight"]
+           "transform_points", "huber_weight", "caratheodory", "fast_caratheodory", "create_gn_set", "gn_set_from_registration"]

@@ -30,6 +30,8 @@ SYMBOLS = {
     "pcr_destroy": (_i, [_vp]),
     "pcr_last_error": (C.c_char_p, [_vp]),
     "pcr_set_target_points": (_i, [_vp, _vp, _i64]),
+    "pcr_append_target_points": (_i, [_vp, _vp, _i64]),
+    "pcr_export_gn_rows": (_i, [_vp, _i, _vp, _d, _vp]),
     "pcr_build_nn_index": (_i, [_vp]),
     "pcr_build_correspondence_lists": (_i, [_vp]),
     "pcr_estimate_normals": (_i, [_vp, _i]),
@@ -205,6 +207,19 @@ class Context:
     def set_target_points(self, pts_f32):
         self._order_after_producer(pts_f32)
         self._check(self._lib.pcr_set_target_points(self._h, _ptr(pts_f32), pts_f32.shape[0]))
+
+    def append_target_points(self, pts_f32):
+        self._order_after_producer(pts_f32)
+        self._check(self._lib.pcr_append_target_points(self._h, _ptr(pts_f32), pts_f32.shape[0]))
+
+    def build_voxels_from_target(self, voxel_size, min_points, with_icov=True):
+        self._check(self._lib.pcr_build_voxels(self._h, None, 0, 0, float(voxel_size), int(min_points), int(bool(with_icov))))
+
+    def export_gn_rows(self, method, T, max_dist, n_scan):
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        rows = np.empty((n_scan, 28), dtype=np.float64)
+        self._check(self._lib.pcr_export_gn_rows(self._h, int(method), _ptr(T), float(max_dist), _ptr(rows)))
+        return rows
 
     def build_nn_index(self):
         self._check(self._lib.pcr_build_nn_index(self._h))

@@ -1448,6 +1448,32 @@ int pcr_set_target_points(pcr_ctx* ctx, const float* xyz, int64_t n) {
     return PCR_OK;
 }
 
+int pcr_append_target_points(pcr_ctx* ctx, const float* xyz, int64_t n) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (!xyz || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_append_target_points: nothing to append");
+    if (ctx->n_tgt <= 0) return fail(ctx, PCR_ERR_STATE, "pcr_append_target_points: no target to append to");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    const long long n_old = ctx->n_tgt, n_new = n_old + n;
+    if (n_new >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "point count exceeds 2^31-1");
+    pcr::DevBuf grown;
+    PCR_CUDA(grown.ensure((size_t)n_new * 12));
+    PCR_CUDA(cudaMemcpyAsync(grown.p, ctx->tgt_xyz.p, (size_t)n_old * 12, cudaMemcpyDeviceToDevice, ctx->stream));   // the old part never leaves the GPU
+    PCR_CUDA(cudaMemcpyAsync((char*)grown.p + (size_t)n_old * 12, xyz, (size_t)n * 12,
+                             is_device_pointer(xyz) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->tgt_xyz.release();
+    ctx->tgt_xyz = grown;
+    ctx->n_tgt = n_new;
+    // every structure over the old target is void (rebuilt by the usual build calls)
+    ctx->tgt_grid.release();
+    ctx->tile_tgt.release();
+    ctx->tgt_shell = ShellLists{};
+    ctx->n_shell_band = ctx->n_shell_entries = 0;
+    ctx->shell_tried = false;
+    ctx->has_normals = false;
+    return PCR_OK;
+}
+
 int pcr_build_nn_index(pcr_ctx* ctx) {
     if (!ctx) return PCR_ERR_ARG;
     if (ctx->n_tgt <= 0) return fail(ctx, PCR_ERR_STATE, "pcr_build_nn_index: target points not set");
@@ -1532,6 +1558,9 @@ int pcr_get_normals(pcr_ctx* ctx, float* normals) {
 
 int pcr_build_voxels(pcr_ctx* ctx, const void* xyz, int64_t n, int is_f64, double voxel_size, int min_points, int with_icov) {
     if (!ctx) return PCR_ERR_ARG;
+    if (!xyz && n == 0 && ctx->n_tgt > 0) {                   // the resident target points (pcr_set_target_points / pcr_append_target_points)
+        xyz = ctx->tgt_xyz.p; n = ctx->n_tgt; is_f64 = 0;
+    }
     if (!xyz || n <= 0) return fail(ctx, PCR_ERR_ARG, "pcr_build_voxels: empty input");
     PCR_CUDA(cudaSetDevice(ctx->device));
     return is_f64 ? build_voxels_impl<double>(ctx, xyz, n, voxel_size, min_points, with_icov)

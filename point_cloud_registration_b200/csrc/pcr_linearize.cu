@@ -363,6 +363,32 @@ __global__ void __launch_bounds__(kLinThreads, MINB) linearize_fused_kernel(cons
 #include "pcr_tile_kernel.cuh"
 namespace pcr {
 
+// Per-correspondence Gauss-Newton rows of the point-to-plane variants: the 28 numbers whose SUM over the
+// scan is the normal-equation record -- upper triangle of J^T J (21), J r (6), r^2 (1), with
+// J = [n^T, (p x R^T n)^T], r = n.(R p + t - q) -- i.e. column i of the reference's
+// caratheodory.create_gn_set(J, r) (caratheodory.py:118-138).  Zeros for slots without correspondence.
+template <int METHOD>
+__global__ void gn_rows_kernel(const LinParams P, double* __restrict__ rows, long long n) {
+    __shared__ BlockShared sh;
+    Pose32 pose;
+    if (!load_pose(P, sh, pose)) return;
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double* out = rows + 28 * i;
+    const int pos = P.prev[i];
+    if (pos < 0) {
+        for (int k = 0; k < 28; ++k) out[k] = 0.0;
+        return;
+    }
+    MatchRec r;
+    fetch_match<METHOD>(P, pos, r);
+    const float px = P.sx[i], py = P.sy[i], pz = P.sz[i];
+    float acc[PCR_NEQ];
+    for (int k = 0; k < PCR_NEQ; ++k) acc[k] = 0.f;
+    accumulate_match<METHOD>(pose, acc, r, px, py, pz);
+    for (int k = 0; k < 28; ++k) out[k] = (double)acc[k];
+}
+
 __global__ void matches_kernel(const int* __restrict__ prev, const float4* __restrict__ pts, long long n, long long* __restrict__ idx) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -1096,6 +1122,41 @@ int pcr_debug_matches(pcr_ctx* ctx, int which, int64_t* idx) {
     PCR_CUDA(cudaMemcpyAsync(idx, di.p, (size_t)ctx->n_scan * 8, cudaMemcpyDeviceToHost, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     di.release();
+    return PCR_OK;
+}
+
+int pcr_export_gn_rows(pcr_ctx* ctx, int method, const double T[16], double max_dist, double* rows) {
+    if (!ctx || !T || !rows) return PCR_ERR_ARG;
+    if (method != PCR_PLANE && method != PCR_VPLANE)
+        return fail(ctx, PCR_ERR_ARG, "pcr_export_gn_rows: scalar-residual methods only (PCR_PLANE, PCR_VPLANE)");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    int rc = check_method(ctx, method);
+    if (rc) return rc;
+    if (ctx->n_scan == 0) return PCR_OK;
+    const int saved = ctx->record_matches;
+    ctx->record_matches = 1;                                  // the tile-stream path parks positions only on request
+    rc = pcr_linearize_async(ctx, method, T, max_dist, 1);
+    ctx->record_matches = saved;
+    if (rc) return rc;
+    LinParams P{};
+    fill_params(ctx, method, max_dist, P);
+    memcpy(P.T_param, T, sizeof(double) * 16);
+    P.use_param_T = 1;
+    const long long n = ctx->n_scan;
+    const bool to_device = is_device_pointer(rows);
+    DevBuf tmp;
+    double* d_rows = rows;
+    if (!to_device) {
+        PCR_CUDA(tmp.ensure((size_t)n * 28 * sizeof(double)));
+        d_rows = tmp.as<double>();
+    }
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    if (method == PCR_PLANE) gn_rows_kernel<PCR_METHOD_PLANE><<<blocks, 256, 0, ctx->stream>>>(P, d_rows, n);
+    else gn_rows_kernel<PCR_METHOD_VPLANE><<<blocks, 256, 0, ctx->stream>>>(P, d_rows, n);
+    PCR_LAUNCH_CHECK();
+    if (!to_device) PCR_CUDA(cudaMemcpyAsync(rows, d_rows, (size_t)n * 28 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    tmp.release();
     return PCR_OK;
 }
 

@@ -23,3 +23,11 @@ class ICP(Registration):
         self._ctx = self.kdtree._ctx
         self._ctx.build_correspondence_lists()           # shell lists streamed by the correspondence pass
         self._target_ready()
+
+    def update_target(self, target):
+        """Append ``target`` to the map (see Registration.update_target)."""
+        if not self._is_target_set:
+            raise ValueError("Target is not set.")
+        self.kdtree.append(target)
+        self.target = self.kdtree.data
+        self._ctx.build_correspondence_lists()

@@ -21,6 +21,18 @@ class KDTree:
         self._ctx.set_target_points(self.data)
         self._ctx.build_nn_index()
 
+    def append(self, points):
+        """Add points to the indexed cloud (the old ones stay on the GPU) and rebuild the index: same
+        result as ``KDTree(concatenate(old, new))``."""
+        new = _lib.as_f32_points(points, "points")
+        self._ctx.append_target_points(new)
+        self._ctx.build_nn_index()
+        if isinstance(self.data, np.ndarray) and isinstance(new, np.ndarray):
+            self.data = np.concatenate([self.data, new])
+        else:
+            self.data = None                       # (partly) device resident: not mirrored on the host
+        self.n += new.shape[0]
+
     def query(self, pts, k=1):
         q = _lib.as_f32_points(pts, "query points")
         dist, idx = self._ctx.knn(q, k)

@@ -32,13 +32,35 @@ class PlaneICP(Registration):
         if kdree is None or norm is None:
             self._ctx.estimate_normals(self.k)
             self._normal = None
+            self._given_normals = False
         else:
             nrm = _lib.as_f32_points(norm, "norm")
             if nrm.shape[0] != self.target.shape[0]:
                 raise ValueError("norm must have one row per target point")
             self._ctx.set_normals(nrm)
             self._normal = norm
+            self._given_normals = True
         self._target_ready()
+
+    def update_target(self, target, norm=None):
+        """Append ``target`` to the map (see Registration.update_target).  Normals: re-estimated over
+        the enlarged map (k-NN neighbourhoods change where old and new points meet), unless the map was
+        set with caller-supplied normals -- then ``norm`` must bring the normals of the new points."""
+        if not self._is_target_set:
+            raise ValueError("Target is not set.")
+        had_own = self._normal is not None and self._given_normals
+        if had_own and norm is None:
+            raise ValueError("this map was set with caller-supplied normals: pass norm= for the new points")
+        self.kdtree.append(target)
+        self.target = self.kdtree.data
+        self._ctx.build_correspondence_lists()
+        if had_own:
+            nrm = np.concatenate([np.asarray(self._normal, dtype=np.float32), np.asarray(norm, dtype=np.float32)])
+            self._ctx.set_normals(np.ascontiguousarray(nrm))
+            self._normal = nrm
+        else:
+            self._ctx.estimate_normals(self.k)
+            self._normal = None
 
     @property
     def normal(self):

@@ -48,7 +48,10 @@ class Registration:
         raise NotImplementedError("set_target is not implemented.")
 
     def update_target(self, target):
-        """Declared but not implemented by the reference either (registration.py:36-43)."""
+        """Add points to the target map without starting over (the reference declares this hook and
+        leaves it unimplemented, registration.py:36-43).  The old part of the map stays on the GPU, the
+        new points are appended and the target structures are rebuilt there; the result is identical to
+        ``set_target(concatenate(old, new))``.  Implemented by the four classes."""
         raise NotImplementedError("update_target is not implemented.")
 
     def linearize(self, cur_T, source):

@@ -39,14 +39,36 @@ class VoxelGrid:
         self._device = device
         self._ctx = None
         self._cache = None
+        self._host64 = None
 
     def set_points(self, points):
-        """voxel.py:104-165 on the GPU (inverse covariances included: they cost nothing extra)."""
+        """voxel.py:104-165 on the GPU (inverse covariances included: they cost nothing extra).
+        float32 clouds stay resident on the GPU so that ``add_points`` can extend them in place."""
         if self._ctx is None:
             self._ctx = _lib.Context(self._device)
-        self._ctx.build_voxels(points, self.voxel_size, self.min_points, with_icov=True)
+        self._host64 = None
+        is_dev = _lib.is_device_array(points)
+        if (is_dev and _lib.DevicePoints(points).dtype == np.float32) or (not is_dev and np.asarray(points).dtype != np.float64):
+            self._ctx.set_target_points(_lib.as_f32_points(points, "points"))
+            self._ctx.build_voxels_from_target(self.voxel_size, self.min_points, with_icov=True)
+        else:
+            # float64 input: the statistics are accumulated from the float64 values (as the reference does)
+            self._ctx.build_voxels(points, self.voxel_size, self.min_points, with_icov=True)
+            self._host64 = None if is_dev else np.asarray(points)
         self._cache = None
         self.kdtree = _MeanIndex(self._ctx)
+
+    def add_points(self, points):
+        """Extend the cloud and rebuild the voxel statistics: same result as
+        ``set_points(concatenate(old, new))`` (per-voxel sums run in point order, old points first)."""
+        if self._ctx is None:
+            raise ValueError("set_points has not been called")
+        if self._host64 is not None:
+            self.set_points(np.concatenate([self._host64, np.asarray(points, dtype=np.float64)]))
+            return
+        self._ctx.append_target_points(_lib.as_f32_points(points, "points"))
+        self._ctx.build_voxels_from_target(self.voxel_size, self.min_points, with_icov=True)
+        self._cache = None
 
     def calc_icov(self):
         """Closed-form inverse covariances (voxel.py:69-102); already built by set_points."""

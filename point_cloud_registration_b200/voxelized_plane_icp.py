@@ -20,3 +20,9 @@ class VPlaneICP(Registration):
         self.voxels.set_points(target)
         self._ctx = self.voxels._ctx
         self._target_ready()
+
+    def update_target(self, target):
+        """Append ``target`` to the map and rebuild the voxel statistics (see Registration.update_target)."""
+        if not self._is_target_set:
+            raise ValueError("Target is not set.")
+        self.voxels.add_points(target)
