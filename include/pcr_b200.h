@@ -215,6 +215,11 @@ int pcr_linearize_async(pcr_ctx* ctx, int method, const double T[16], double max
  * (default on); 0 falls back to the general grid search everywhere (A/B and test hook). */
 int pcr_set_voxel_lists(pcr_ctx* ctx, int enable);
 int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries);
+/* Opt-in (PCR_VOXEL_SHELL=1 when the voxels are built): the correspondence pass of VPlaneICP / NDT
+ * streams margin-ordered shell lists over the kept voxel means (the structure pcr_shell_list_stats
+ * describes for target points) instead of the exact candidate lists above.  Measured: equal on late
+ * iterations, slower on the first ones (profiles/r2_notes.md). */
+int pcr_voxel_shell_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries, double* margin_cells);
 /* Target-point correspondences (ICP / PlaneICP) are read from per-cell "shell lists" built with
  * the NN index (every point within `margin` cell edges of the cell, ordered by its distance to
  * the cell; default on, margin 2 reduced until the lists fit the memory cap); 0 walks the brick

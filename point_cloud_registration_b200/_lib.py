@@ -65,6 +65,7 @@ SYMBOLS = {
     "pcr_debug_matches": (_i, [_vp, _i, _vp]),
     "pcr_set_voxel_lists": (_i, [_vp, _i]),
     "pcr_voxel_list_stats": (_i, [_vp, _pi64, _pi64]),
+    "pcr_voxel_shell_stats": (_i, [_vp, _vp, _vp, _vp]),
     "pcr_index_stats": (_i, [_vp, _i, C.POINTER(_d), _pi64, _pi64, _pi64]),
     "pcr_set_path": (_i, [_vp, _i]),
     "pcr_tile_stats": (_i, [_vp, _i, C.POINTER(_d), _pi64, _pi64, _pi64]),
@@ -288,6 +289,11 @@ class Context:
         a, b = C.c_int64(), C.c_int64()
         self._check(self._lib.pcr_voxel_list_stats(self._h, C.byref(a), C.byref(b)))
         return dict(band_cells=a.value, entries=b.value)
+
+    def voxel_shell_stats(self):
+        a, b, m = C.c_int64(), C.c_int64(), C.c_double()
+        self._check(self._lib.pcr_voxel_shell_stats(self._h, C.byref(a), C.byref(b), C.byref(m)))
+        return dict(band_cells=a.value, entries=b.value, margin_cells=m.value, bytes=b.value * 17)
 
     def set_shell_lists(self, enable):
         self._check(self._lib.pcr_set_shell_lists(self._h, int(bool(enable))))

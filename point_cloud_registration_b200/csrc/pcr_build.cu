@@ -886,17 +886,37 @@ struct U32ToU64 {
     __host__ __device__ unsigned long long operator()(uint32_t v) const { return (unsigned long long)v; }
 };
 
-static int build_shell_lists(pcr_ctx* ctx) {
-    Grid& g = ctx->tgt_grid;
-    ctx->tgt_shell = ShellLists{};
-    ctx->n_shell_band = ctx->n_shell_entries = 0;
-    ctx->shell_dmax_used = 0.0;
+// `which` = 0: lists over the target points (ICP / PlaneICP), 1: over the kept voxel means (VPlaneICP / NDT:
+// one mean per cell at most, so a list is the margin-ordered set of means around the cell and a query
+// usually stops after its first group -- the exact candidate lists of round 1 made every query evaluate
+// its cell's whole candidate set, ~20 means, through an index indirection).
+static int build_shell_lists(pcr_ctx* ctx, int which = 0) {
+    Grid& g = which == 0 ? ctx->tgt_grid : ctx->vox_grid;
+    ShellLists& view = which == 0 ? ctx->tgt_shell : ctx->vox_shell;
+    DevBuf& b_bricks = which == 0 ? ctx->shell_bricks : ctx->vshell_bricks;
+    DevBuf& b_start = which == 0 ? ctx->shell_start : ctx->vshell_start;
+    DevBuf& b_pts = which == 0 ? ctx->shell_pts : ctx->vshell_pts;
+    DevBuf& b_margin2 = which == 0 ? ctx->shell_margin2 : ctx->vshell_margin2;
+    long long& n_band_out = which == 0 ? ctx->n_shell_band : ctx->n_vshell_band;
+    long long& n_entries_out = which == 0 ? ctx->n_shell_entries : ctx->n_vshell_entries;
+    double& dmax_used = which == 0 ? ctx->shell_dmax_used : ctx->vshell_dmax_used;
+    view = ShellLists{};
+    n_band_out = n_entries_out = 0;
+    dmax_used = 0.0;
     if (!g.built || g.view.n_pts == 0) return PCR_OK;
-    if (const char* e = getenv("PCR_SHELL_LISTS")) if (atoi(e) == 0) return PCR_OK;
+    if (which == 0) {
+        if (const char* e = getenv("PCR_SHELL_LISTS")) if (atoi(e) == 0) return PCR_OK;
+    } else {
+        // measured (profiles/r2_notes.md): same late-iteration time as the exact candidate lists, +4 % on NDT 10M,
+        // but the first two iterations of VPlaneICP 10M take 1.7x longer (queries displaced beyond the margin fall
+        // back to the grid walk; the candidate lists cover them) -- opt-in
+        const char* e = getenv("PCR_VOXEL_SHELL");
+        if (!e || atoi(e) == 0) return PCR_OK;
+    }
     const GridView& G = g.view;
     const unsigned long long nbricks = (unsigned long long)G.bnx * G.bny * G.bnz;
-    PCR_CUDA(ctx->shell_bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
-    BrickRec* lb = ctx->shell_bricks.as<BrickRec>();
+    PCR_CUDA(b_bricks.ensure((size_t)nbricks * sizeof(BrickRec)));
+    BrickRec* lb = b_bricks.as<BrickRec>();
     const long long nthreads = (long long)nbricks * 64;
     // the requested margin first, then smaller ones until the lists fit the memory cap
     const double tries[5] = {ctx->shell_dmax_frac, 2.0, 1.5, 1.0, 0.5};
@@ -922,7 +942,7 @@ static int build_shell_lists(pcr_ctx* ctx) {
         brick_base_set_kernel<<<blocks_for((long long)nbricks, 256), 256, 0, ctx->stream>>>(lb, nbricks, bbase);
         PCR_LAUNCH_CHECK();
         PCR_CUDA(ctx->tmp_b.ensure(((size_t)n_band + 1) * 4));
-        PCR_CUDA(ctx->shell_start.ensure(((size_t)n_band + 1) * 4));
+        PCR_CUDA(b_start.ensure(((size_t)n_band + 1) * 4));
         uint32_t* counts = ctx->tmp_b.as<uint32_t>();
         PCR_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_band + 1) * 4, ctx->stream));
         shell_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, dmax, R, counts, nullptr, nullptr, nullptr);
@@ -944,27 +964,27 @@ static int build_shell_lists(pcr_ctx* ctx) {
         // the margin of three cells (2.5x the memory of two) is for targets whose lists stay small
         const double cap_gib = frac > 2.0 ? std::min(ctx->shell_max_gib, ctx->shell_wide_gib) : ctx->shell_max_gib;
         if (total_groups >= (1ull << 32) - 8ull || gib > cap_gib) continue;           // too large: try a smaller margin
-        rc = exclusive_sum_u32(ctx, counts, ctx->shell_start.as<uint32_t>(), (long long)n_band + 1);
+        rc = exclusive_sum_u32(ctx, counts, b_start.as<uint32_t>(), (long long)n_band + 1);
         if (rc) return rc;
         const unsigned long long n_entries = total;
-        PCR_CUDA(ctx->shell_pts.ensure(((size_t)n_entries + 4) * sizeof(float4)));
-        PCR_CUDA(ctx->shell_margin2.ensure(((size_t)total_groups + 1) * 4));
-        pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(ctx->shell_pts.as<float4>(), (long long)n_entries, nullptr, 0);
+        PCR_CUDA(b_pts.ensure(((size_t)n_entries + 4) * sizeof(float4)));
+        PCR_CUDA(b_margin2.ensure(((size_t)total_groups + 1) * 4));
+        pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(b_pts.as<float4>(), (long long)n_entries, nullptr, 0);
         PCR_LAUNCH_CHECK();
-        shell_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, dmax, R, nullptr, ctx->shell_start.as<uint32_t>(),
-                                                                                    ctx->shell_pts.as<float4>(), ctx->shell_margin2.as<float>());
+        shell_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, dmax, R, nullptr, b_start.as<uint32_t>(),
+                                                                                    b_pts.as<float4>(), b_margin2.as<float>());
         PCR_LAUNCH_CHECK();
         PCR_CUDA(cudaStreamSynchronize(ctx->stream));
-        ctx->tgt_shell.bricks = ctx->shell_bricks.as<uint4>();
-        ctx->tgt_shell.start = ctx->shell_start.as<uint32_t>();
-        ctx->tgt_shell.pts = ctx->shell_pts.as<float4>();
-        ctx->tgt_shell.margin2 = ctx->shell_margin2.as<float>();
+        view.bricks = b_bricks.as<uint4>();
+        view.start = b_start.as<uint32_t>();
+        view.pts = b_pts.as<float4>();
+        view.margin2 = b_margin2.as<float>();
         const float cov = fmaxf(dmax - G.slack * G.h, 0.0f);
-        ctx->tgt_shell.covered2 = cov * cov;
-        ctx->tgt_shell.block_r = (double)dmax >= 1.7320508 * (double)G.h * 1.0001 ? 1 : 0;
-        ctx->n_shell_band = n_band;
-        ctx->n_shell_entries = (long long)n_entries;
-        ctx->shell_dmax_used = frac;
+        view.covered2 = cov * cov;
+        view.block_r = (double)dmax >= 1.7320508 * (double)G.h * 1.0001 ? 1 : 0;
+        n_band_out = n_band;
+        n_entries_out = (long long)n_entries;
+        dmax_used = frac;
         return PCR_OK;
     }
     return PCR_OK;                                            // nothing fits: the general search stays in charge
@@ -987,6 +1007,7 @@ static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     ctx->vox_grid_epoch++;
     ctx->vox_grid.release();
     ctx->tile_vox.release();
+    ctx->vox_shell = ShellLists{};
     ctx->n_vox = n_keep; ctx->n_vox_all = F.n_seg; ctx->voxel_size = voxel_size;
     const size_t nk = n_keep ? n_keep : 1;
     PCR_CUDA(ctx->vox_mean.ensure(nk * 3 * 8));
@@ -1031,8 +1052,12 @@ static int build_voxels_impl(pcr_ctx* ctx, const void* xyz, long long n, double 
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     F.release();
     if (ctx->use_tile) rc = ensure_tile_index(ctx, PCR_VPLANE);   // row grid over the kept means + both payloads
-    else rc = build_voxel_lists(ctx);
+    else rc = build_voxel_lists(ctx);                             // exact candidate lists (VoxelGrid.query)
     if (rc) return rc;
+    if (!ctx->use_tile) {
+        rc = build_shell_lists(ctx, 1);                           // margin-ordered lists streamed by the correspondence pass
+        if (rc) return rc;
+    }
     ctx->has_voxels = true;
     ctx->has_icov = with_icov != 0;
     return PCR_OK;
@@ -1416,6 +1441,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
     ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release();
     ctx->shell_bricks.release(); ctx->shell_start.release(); ctx->shell_pts.release(); ctx->shell_margin2.release();
+    ctx->vshell_bricks.release(); ctx->vshell_start.release(); ctx->vshell_pts.release(); ctx->vshell_margin2.release();
     ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();
     ctx->tile_tgt.release(); ctx->tile_vox.release(); ctx->scan_hint.release(); ctx->tile_scratch.release();
     ctx->partials.release(); ctx->state.release();
@@ -1703,6 +1729,14 @@ int pcr_voxel_list_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries) {
     if (!ctx) return PCR_ERR_ARG;
     if (band_cells) *band_cells = ctx->n_band_cells;
     if (entries) *entries = ctx->n_list_entries;
+    return PCR_OK;
+}
+
+int pcr_voxel_shell_stats(pcr_ctx* ctx, int64_t* band_cells, int64_t* entries, double* margin_cells) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (band_cells) *band_cells = ctx->n_vshell_band;
+    if (entries) *entries = ctx->n_vshell_entries;
+    if (margin_cells) *margin_cells = ctx->vshell_dmax_used;
     return PCR_OK;
 }
 

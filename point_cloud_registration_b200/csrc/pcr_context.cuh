@@ -109,6 +109,10 @@ struct pcr_ctx {
     pcr::Grid vox_grid;           // NN index over kept voxel means (payload = voxel ordinal)
     pcr::DevBuf vox_lbricks, vox_list_start, vox_list_idx;   // per-cell candidate lists over the voxel means
     pcr::CandLists vox_lists{};   // null pointers = not built
+    pcr::DevBuf vshell_bricks, vshell_start, vshell_pts, vshell_margin2;   // margin-ordered shell lists over the kept voxel means
+    pcr::ShellLists vox_shell{};  // null pointers = not built
+    long long n_vshell_band = 0, n_vshell_entries = 0;
+    double vshell_dmax_used = 0.0;
     long long n_band_cells = 0, n_list_entries = 0;
     int use_voxel_lists = 1;
     int list_dilate = 3, list_radius = 5;   // candidate-list band dilation / build neighbourhood radius (cells)

@@ -86,34 +86,77 @@ PCR_HD void icov_closed_form(const double* cov, double* icov) {
 
 // Solve H x = rhs (6x6, row major, general) by LU with partial pivoting.
 // Returns 0 on success, 1 if an exactly-zero pivot is met (np.linalg.solve -> LinAlgError).
+// Every loop is unrolled and the row exchange is written as compare-and-swap against each candidate
+// row, so that all indices are compile-time constants and the 6x7 tableau lives in registers: on the
+// GPU this runs in ONE thread of the last block while the rest of the device waits (with a
+// dynamically indexed tableau in local memory it was half of the accumulate kernel's duration).
 PCR_HD int solve6(const double* Hin, const double* rhs, double* x) {
     double M[6][7];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int i = 0; i < 6; ++i) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (int j = 0; j < 6; ++j) M[i][j] = Hin[i * 6 + j];
         M[i][6] = rhs[i];
     }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int col = 0; col < 6; ++col) {
         int piv = col;
         double best = fabs(M[col][col]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (int r = col + 1; r < 6; ++r) {
-            double v = fabs(M[r][col]);
+            const double v = fabs(M[r][col]);
             if (v > best) { best = v; piv = r; }
         }
         if (best == 0.0 || best != best) return 1;
-        if (piv != col)
-            for (int j = col; j < 7; ++j) { double tmp = M[col][j]; M[col][j] = M[piv][j]; M[piv][j] = tmp; }
-        double inv = 1.0 / M[col][col];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
         for (int r = col + 1; r < 6; ++r) {
-            double fac = M[r][col] * inv;
-            if (fac == 0.0) continue;
-            for (int j = col + 1; j < 7; ++j) M[r][j] -= fac * M[col][j];
+            if (piv == r) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = col; j < 7; ++j) { const double tmp = M[col][j]; M[col][j] = M[r][j]; M[r][j] = tmp; }
+            }
+        }
+        const double inv = 1.0 / M[col][col];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int r = col + 1; r < 6; ++r) {
+            const double fac = M[r][col] * inv;
+            if (fac != 0.0) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+                for (int j = col + 1; j < 7; ++j) M[r][j] -= fac * M[col][j];
+            }
         }
     }
+    double y[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (int i = 5; i >= 0; --i) {
         double acc = M[i][6];
-        for (int j = i + 1; j < 6; ++j) acc -= M[i][j] * x[j];
-        x[i] = acc / M[i][i];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = i + 1; j < 6; ++j) acc -= M[i][j] * y[j];
+        y[i] = acc / M[i][i];
     }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) x[i] = y[i];
     return 0;
 }
 
@@ -130,7 +173,9 @@ PCR_HD void so3_exp(const double* w, double* R) {
     }
     const double th = sqrt(th2);
     const double kx = x / th, ky = y / th, kz = z / th;
-    const double s = sin(th), c1 = 1.0 - cos(th);
+    double s, c;
+    sincos(th, &s, &c);
+    const double c1 = 1.0 - c;
     // K = hat(k), KK = K*K
     const double K[9] = {0, -kz, ky, kz, 0, -kx, -ky, kx, 0};
     for (int i = 0; i < 3; ++i)

@@ -245,14 +245,15 @@ __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32
         transform32(pose, px, py, pz, qx, qy, qz);
         bool settled = false;
         if (lists) {
-            if (kVoxel) {
-                settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);
-            } else {
+            if (P.use_shell) {
+                // margin-ordered shell list of the query's cell (target points, or kept voxel means)
                 const int st = shell_scan(P.grid, P.shell, qx, qy, qz, P.max_d2, d2, pos);
                 settled = st != 0;
                 // list exhausted before the best was proven nearest: the search resumes outside
                 // the block of cells the list covered, pruned by the list's best
                 if (st == 2) pos = shell_continue_nn(P.grid, P.shell, qx, qy, qz, d2, pos);
+            } else if (kVoxel) {
+                settled = list_nn(P.grid, P.lists, qx, qy, qz, P.max_d2, d2, pos);   // exact candidate list (A/B: PCR_VOXEL_SHELL=0)
             }
         }
         if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2, lists && P.ball_first);
@@ -272,7 +273,7 @@ template <int METHOD, bool DYNAMIC>
 __device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32& pose) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
     const int lane = threadIdx.x & 31;
-    const bool lists = kVoxel ? (P.use_lists != 0) : (P.use_shell != 0);
+    const bool lists = P.use_shell != 0 || (kVoxel && P.use_lists != 0);
     if (DYNAMIC) {
         const int rows_total = (int)(P.n_pad >> 5);
         for (;;) {
@@ -305,7 +306,8 @@ __device__ __forceinline__ void accumulate_pass(const LinParams& P, BlockShared&
     const long long stride = (long long)gridDim.x * kLinThreads;
     // float64 accumulators: per-point terms are float32 products (as the reference's float32 geometry), every
     // SUM is float64 -- the reference sums in float64 after the gather (ndt.py:39-56), and records no longer
-    // depend on how the scan is split over threads or GPUs beyond 1e-13
+    // depend on how the scan is split over threads or GPUs beyond 1e-13.  (Measured and dropped: summing the
+    // four slots of a trip in float32 first -- no faster, and align() then differs by 4e-8 between scan orders.)
     double acc[NACC];
 #pragma unroll
     for (int i = 0; i < NACC; ++i) acc[i] = 0.0;
@@ -644,8 +646,8 @@ static void fill_params(pcr_ctx* ctx, int method, double max_dist, LinParams& P)
     P.prev = ctx->scan_prev.as<int>();
     P.lists = ctx->vox_lists;
     P.use_lists = (method == PCR_VPLANE || method == PCR_NDT) && ctx->use_voxel_lists && ctx->vox_lists.bricks != nullptr;
-    P.shell = ctx->tgt_shell;
-    P.use_shell = (method == PCR_ICP || method == PCR_PLANE) && ctx->use_shell_lists && ctx->tgt_shell.bricks != nullptr;
+    P.shell = (method == PCR_ICP || method == PCR_PLANE) ? ctx->tgt_shell : ctx->vox_shell;
+    P.use_shell = ((method == PCR_ICP || method == PCR_PLANE) ? ctx->use_shell_lists : ctx->use_voxel_lists) && P.shell.bricks != nullptr;
     P.ball_first = ctx->ball_first;
     // rows per fetch: about 16 fetches per resident warp (one device-wide counter serves them all;
     // a fetch per row would make it the bottleneck of a 10M-point scan), at least 1

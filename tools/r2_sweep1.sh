@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2 sweep 1: tile-stream tunables on C2 (and one C3/C4 line each)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "shell_lists or linearize_10k or align_10k or scheduling" > gpurun_out/r2_s1_tests.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "voxel or linearize_10k or align_10k or scheduling or slab_200k or properties" > gpurun_out/r2_s1_tests.log 2>&1
 tail -2 gpurun_out/r2_s1_tests.log
 run() {  # name, workload, env...
   name=$1; wl=$2; shift 2
@@ -16,7 +16,9 @@ except Exception as e:
     print(n, "failed", e, flush=True)
 PY
 }
-run c2_lists_m3 c2 A=1
-run c2_lists_m2 c2 PCR_SHELL_DMAX=2
-run c2_lists_m3_ppc16 c2 PCR_TARGET_PPC=16
-run c2_lists_m3_ppc32 c2 PCR_TARGET_PPC=32
+run c2_final c2 A=1
+run c3_vshell c3 A=1
+run c3_candlists c3 PCR_VOXEL_SHELL=0
+run c4_vshell c4 A=1
+run c4_candlists c4 PCR_VOXEL_SHELL=0
+run c2i_final c2i A=1
