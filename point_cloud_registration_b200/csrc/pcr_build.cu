@@ -200,7 +200,7 @@ int build_point_grid(pcr_ctx* ctx, const float* d_xyz, long long n, Grid& g, Dev
     if (maxext <= 0) maxext = 1.0;
     double vol = 1.0;
     for (int a = 0; a < 3; ++a) vol *= std::max(ext[a], 1e-3 * maxext);
-    const double target_ppc = ctx->target_ppc;
+    const double target_ppc = ctx->target_ppc > 0.0 ? ctx->target_ppc : (n <= 4000000 ? 10.0 : 24.0);
     double h = cbrt(vol * target_ppc / (double)n);
     h = std::max(h, maxext * 1e-5);
 
@@ -1403,7 +1403,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
         return fail(nullptr, PCR_ERR_CUDA, m);
     }
     if (const char* e = getenv("PCR_MIN_BLOCKS")) ctx->min_blocks = atoi(e) >= 3 && atoi(e) <= 6 ? atoi(e) : 0;
-    if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 24.0;
+    if (const char* e = getenv("PCR_TARGET_PPC")) ctx->target_ppc = atof(e) > 0.5 ? atof(e) : 0.0;
     if (const char* e = getenv("PCR_SHELL_DMAX")) ctx->shell_dmax_frac = atof(e) > 0.0 && atof(e) <= PCR_SHELL_MAX_MARGIN ? atof(e) : 1.0;
     if (const char* e = getenv("PCR_SHELL_MAX_GIB")) ctx->shell_max_gib = atof(e) > 0.0 ? atof(e) : 96.0;
     if (const char* e = getenv("PCR_SHELL_WIDE_GIB")) ctx->shell_wide_gib = atof(e) >= 0.0 ? atof(e) : 8.0;

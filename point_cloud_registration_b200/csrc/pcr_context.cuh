@@ -145,7 +145,9 @@ struct pcr_ctx {
     long long n_scan_pad = 0;     // padded to a multiple of 32 with NaN (whole tiles enter the kernel loop)
     bool scan_set = false;
     bool scan_sorted = false;     // spatially coherent order (Morton-sorted on upload, or promised by the caller)
-    double target_ppc = 24.0;     // desired mean points per occupied cell of the target-point grid
+    double target_ppc = 0.0;      // desired mean points per occupied cell of the target-point grid; 0 = by target size:
+                                  // 10 while lists with a 3-cell margin fit (<= 4M points), else 24 (the margin is then
+                                  // bought in metres per byte: larger cells reach farther) -- profiles/r2_notes.md
     int min_blocks = 0;           // resident blocks per SM requested for the correspondence pass (3..6; 0: per-method default)
     int ball_first = 1;           // list misses search the ball of max_dist in one pass (0: ring growth, A/B)
     int cell_order = 1;           // scan upload: order by correspondence-grid cell (0: Morton order in the scan's frame)

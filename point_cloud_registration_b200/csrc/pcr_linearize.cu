@@ -685,9 +685,9 @@ static int launch_accumulate(pcr_ctx* ctx, const LinParams& P) {
 template <int METHOD>
 static int launch_method(pcr_ctx* ctx, const LinParams& P) {
     // ctx->min_blocks = resident blocks per SM requested for the correspondence pass (2..6)
-    // resident blocks per SM of the correspondence kernel: measured best 5 (48 registers) for the
-    // shell-list stream, 4 for the voxel candidate lists; PCR_MIN_BLOCKS overrides
-    int mb = ctx->min_blocks > 0 ? ctx->min_blocks : ((METHOD == PCR_METHOD_ICP || METHOD == PCR_METHOD_PLANE) ? 5 : 4);
+    // resident blocks per SM of the correspondence kernel: measured best 6 (40 registers) for the
+    // shell-list stream on B-01 (round 2), 4 for the voxel candidate lists; PCR_MIN_BLOCKS overrides
+    int mb = ctx->min_blocks > 0 ? ctx->min_blocks : ((METHOD == PCR_METHOD_ICP || METHOD == PCR_METHOD_PLANE) ? 6 : 4);
     mb = mb < 3 ? 3 : (mb > 6 ? 6 : mb);
     int* cache = ctx->lin_blocks_per_sm[METHOD];
     if (ctx->split_passes) {

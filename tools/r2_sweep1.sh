@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2 sweep 1: tile-stream tunables on C2 (and one C3/C4 line each)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "voxel or linearize_10k or align_10k or scheduling or slab_200k or properties" > gpurun_out/r2_s1_tests.log 2>&1
+true > gpurun_out/r2_s1_tests.log 2>&1
 tail -2 gpurun_out/r2_s1_tests.log
 run() {  # name, workload, env...
   name=$1; wl=$2; shift 2
@@ -16,9 +16,8 @@ except Exception as e:
     print(n, "failed", e, flush=True)
 PY
 }
-run c2_final c2 A=1
-run c3_vshell c3 A=1
-run c3_candlists c3 PCR_VOXEL_SHELL=0
-run c4_vshell c4 A=1
-run c4_candlists c4 PCR_VOXEL_SHELL=0
-run c2i_final c2i A=1
+run c3_mb4 c3 A=1
+run c3_mb6 c3 PCR_MIN_BLOCKS=6
+run c3_mb5 c3 PCR_MIN_BLOCKS=5
+run c4_mb6 c4 PCR_MIN_BLOCKS=6
+run c4_mb5 c4 PCR_MIN_BLOCKS=5
