@@ -35,18 +35,21 @@ PCR_HD void transform32(const Pose32& P, float px, float py, float pz, float& sx
 //      [13..15] sum p x (R r), [16] sum r.r
 template <typename A>
 PCR_HD void accum_icp(A* acc, const Pose32& P, float px, float py, float pz, float rx, float ry, float rz) {
-    acc[0] += 1.0f;
-    acc[1] += px; acc[2] += py; acc[3] += pz;
-    acc[4] += px * px; acc[5] += py * py; acc[6] += pz * pz;
-    acc[7] += px * py; acc[8] += px * pz; acc[9] += py * pz;
-    acc[10] += rx; acc[11] += ry; acc[12] += rz;
+    // (operands are cast to the accumulator type BEFORE the product: with float64 accumulators every term is
+    //  one DFMA on converted operands instead of a float product, a conversion and an add)
+    const A X = (A)px, Y = (A)py, Z = (A)pz;
+    acc[0] += (A)1;
+    acc[1] += X; acc[2] += Y; acc[3] += Z;
+    acc[4] += X * X; acc[5] += Y * Y; acc[6] += Z * Z;
+    acc[7] += X * Y; acc[8] += X * Z; acc[9] += Y * Z;
+    acc[10] += (A)rx; acc[11] += (A)ry; acc[12] += (A)rz;
     const float vx = P.r[0] * rx + P.r[1] * ry + P.r[2] * rz;      // v = R r   (quirk Q1)
     const float vy = P.r[3] * rx + P.r[4] * ry + P.r[5] * rz;
     const float vz = P.r[6] * rx + P.r[7] * ry + P.r[8] * rz;
-    acc[13] += py * vz - pz * vy;
-    acc[14] += pz * vx - px * vz;
-    acc[15] += px * vy - py * vx;
-    acc[16] += rx * rx + ry * ry + rz * rz;
+    acc[13] += Y * (A)vz - Z * (A)vy;
+    acc[14] += Z * (A)vx - X * (A)vz;
+    acc[15] += X * (A)vy - Y * (A)vx;
+    acc[16] += (A)rx * (A)rx + (A)ry * (A)ry + (A)rz * (A)rz;
 }
 
 // raw[17] (reduced, float64) + current T -> rec[29]
@@ -84,6 +87,12 @@ PCR_HD void accum_plane(A* acc, const Pose32& P, float px, float py, float pz,
     J[3] = py * az - pz * ay;
     J[4] = pz * ax - px * az;
     J[5] = px * ay - py * ax;
+    A Ja[6];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < 6; ++i) Ja[i] = (A)J[i];
+    const A ra = (A)r;
     int k = 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -92,14 +101,14 @@ PCR_HD void accum_plane(A* acc, const Pose32& P, float px, float py, float pz,
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = i; j < 6; ++j) acc[k++] += J[i] * J[j];
+        for (int j = i; j < 6; ++j) acc[k++] += Ja[i] * Ja[j];
     }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int i = 0; i < 6; ++i) acc[21 + i] += J[i] * r;
-    acc[27] += r * r;
-    acc[28] += 1.0f;
+    for (int i = 0; i < 6; ++i) acc[21 + i] += Ja[i] * ra;
+    acc[27] += ra * ra;
+    acc[28] += (A)1;
 }
 
 // ---- NDT: d = src - mu, J = [I, -R hat(p)], weight W = Sigma^-1 (symmetric, 6 unique) -------

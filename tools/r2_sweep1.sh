@@ -16,8 +16,6 @@ except Exception as e:
     print(n, "failed", e, flush=True)
 PY
 }
-run c3_mb4 c3 A=1
-run c3_mb6 c3 PCR_MIN_BLOCKS=6
-run c3_mb5 c3 PCR_MIN_BLOCKS=5
-run c4_mb6 c4 PCR_MIN_BLOCKS=6
-run c4_mb5 c4 PCR_MIN_BLOCKS=5
+run c2_dfma c2 A=1
+run c3_dfma c3 A=1
+run c2i_dfma c2i A=1
