@@ -653,7 +653,7 @@ __global__ void brick_base_set_kernel(BrickRec* __restrict__ bricks, unsigned lo
 template <bool FILL>
 __global__ void list_build_kernel(GridView G, const BrickRec* __restrict__ lbricks, unsigned long long nbricks, float* __restrict__ D2s,
                                   uint32_t* __restrict__ counts, const uint32_t* __restrict__ list_start, uint32_t* __restrict__ list_idx,
-                                  int kListRadius) {
+                                  float4* __restrict__ list_pts, int kListRadius) {
     const unsigned long long tid = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
     const unsigned long long b = tid >> 6;
     const int bit = (int)(tid & 63ull);
@@ -709,7 +709,11 @@ __global__ void list_build_kernel(GridView G, const BrickRec* __restrict__ lbric
                                 const float ay = fmaxf(fmaxf(fy - gy, gy - fy - 1.0f), 0.0f);
                                 const float az = fmaxf(fmaxf(fz - gz, gz - fz - 1.0f), 0.0f);
                                 if (ax * ax + ay * ay + az * az <= lim2) {
-                                    if (FILL) list_idx[w++] = p;
+                                    if (FILL) {
+                                        list_idx[w] = p;
+                                        if (list_pts) list_pts[w] = make_float4(mp.x, mp.y, mp.z, __uint_as_float(p));
+                                        ++w;
+                                    }
                                     ++n_out;
                                 }
                             }
@@ -753,7 +757,7 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     float* D2s = ctx->tmp_c.as<float>();
     PCR_CUDA(cudaMemsetAsync(counts, 0, ((size_t)n_band + 1) * 4, ctx->stream));
     const long long nthreads = (long long)nbricks * 64;
-    list_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, counts, nullptr, nullptr, ctx->list_radius);
+    list_build_kernel<false><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, counts, nullptr, nullptr, nullptr, ctx->list_radius);
     PCR_LAUNCH_CHECK();
     rc = exclusive_sum_u32(ctx, counts, ctx->vox_list_start.as<uint32_t>(), (long long)n_band + 1);
     if (rc) return rc;
@@ -763,13 +767,24 @@ static int build_voxel_lists(pcr_ctx* ctx) {
     PCR_CUDA(ctx->vox_list_idx.ensure(((size_t)n_entries + 4) * 4));
     pad_tail_kernel<<<1, 32, 0, ctx->stream>>>(nullptr, (long long)G.n_pts, ctx->vox_list_idx.as<uint32_t>(), (long long)n_entries);
     PCR_LAUNCH_CHECK();
+    // the candidate means inline next to their indices (one load per candidate instead of two dependent ones),
+    // unless that copy would be large (PCR_LIST_INLINE=0 disables it)
+    float4* inline_pts = nullptr;
+    {
+        const char* e = getenv("PCR_LIST_INLINE");
+        if ((!e || atoi(e) != 0) && (double)n_entries * 16.0 <= 4.0 * 1024.0 * 1024.0 * 1024.0) {
+            PCR_CUDA(ctx->vox_list_pts.ensure(((size_t)n_entries + 4) * sizeof(float4)));
+            inline_pts = ctx->vox_list_pts.as<float4>();
+        }
+    }
     list_build_kernel<true><<<blocks_for(nthreads, 128), 128, 0, ctx->stream>>>(G, lb, nbricks, D2s, nullptr, ctx->vox_list_start.as<uint32_t>(),
-                                                                               ctx->vox_list_idx.as<uint32_t>(), ctx->list_radius);
+                                                                               ctx->vox_list_idx.as<uint32_t>(), inline_pts, ctx->list_radius);
     PCR_LAUNCH_CHECK();
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     ctx->vox_lists.bricks = ctx->vox_lbricks.as<uint4>();
     ctx->vox_lists.list_start = ctx->vox_list_start.as<uint32_t>();
     ctx->vox_lists.list_idx = ctx->vox_list_idx.as<uint32_t>();
+    ctx->vox_lists.list_pts = inline_pts;
     ctx->n_band_cells = n_band;
     ctx->n_list_entries = n_entries;
     return PCR_OK;
@@ -1439,7 +1454,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->tgt_xyz.release(); ctx->tgt_grid.release(); ctx->tgt_nrm_sorted.release(); ctx->tgt_nrm_orig.release(); ctx->tgt_pn.release();
     ctx->vox_mean.release(); ctx->vox_cov.release(); ctx->vox_norm.release(); ctx->vox_icov.release(); ctx->vox_count.release();
     ctx->vox_grid.release(); ctx->vox_rec_plane.release(); ctx->vox_rec_ndt.release();
-    ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release();
+    ctx->vox_lbricks.release(); ctx->vox_list_start.release(); ctx->vox_list_idx.release(); ctx->vox_list_pts.release();
     ctx->shell_bricks.release(); ctx->shell_start.release(); ctx->shell_pts.release(); ctx->shell_margin2.release();
     ctx->vshell_bricks.release(); ctx->vshell_start.release(); ctx->vshell_pts.release(); ctx->vshell_margin2.release();
     ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();

@@ -158,6 +158,8 @@ struct CandLists {
     const uint4* bricks;         // (band mask lo, hi, ordinal of first band cell, unused), same brick layout as the grid
     const uint32_t* list_start;  // [n_band + 1]
     const uint32_t* list_idx;    // positions in GridView::pts
+    const float4* list_pts;      // optional: the same entries with the point inline (x, y, z, position bits) -- one
+                                 // load per candidate instead of an index load and a dependent gather
 };
 
 // Per-cell "shell lists" over the target-point grid.  For every band cell C (within Chebyshev

@@ -107,7 +107,7 @@ struct pcr_ctx {
     double voxel_size = 0.0;
     pcr::DevBuf vox_mean, vox_cov, vox_norm, vox_icov, vox_count;   // double[3n], [9n], [3n], [9n], int64[n]
     pcr::Grid vox_grid;           // NN index over kept voxel means (payload = voxel ordinal)
-    pcr::DevBuf vox_lbricks, vox_list_start, vox_list_idx;   // per-cell candidate lists over the voxel means
+    pcr::DevBuf vox_lbricks, vox_list_start, vox_list_idx, vox_list_pts;   // per-cell candidate lists over the voxel means
     pcr::CandLists vox_lists{};   // null pointers = not built
     pcr::DevBuf vshell_bricks, vshell_start, vshell_pts, vshell_margin2;   // margin-ordered shell lists over the kept voxel means
     pcr::ShellLists vox_shell{};  // null pointers = not built

@@ -407,12 +407,22 @@ PCR_HD bool list_nn(const GridView& G, const CandLists& L, float qx, float qy, f
     if (s == e) return false;
     float best = max_d2;
     int pos = -1;
-    for (uint32_t k = s; k < e; ++k) {
-        const uint32_t p = L.list_idx[k];
-        const float4 t = G.pts[p];
-        const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
-        const float d2 = dist2_rn(ex, ey, ez);
-        if (d2 < best) { best = d2; pos = (int)p; }
+    if (L.list_pts) {
+        uint32_t bk = 0xffffffffu;
+        for (uint32_t k = s; k < e; ++k) {
+            const float4 t = L.list_pts[k];
+            const float d2 = dist2_rn(t.x - qx, t.y - qy, t.z - qz);
+            if (d2 < best) { best = d2; bk = k; }
+        }
+        if (bk != 0xffffffffu) pos = (int)L.list_idx[bk];
+    } else {
+        for (uint32_t k = s; k < e; ++k) {
+            const uint32_t p = L.list_idx[k];
+            const float4 t = G.pts[p];
+            const float ex = t.x - qx, ey = t.y - qy, ez = t.z - qz;
+            const float d2 = dist2_rn(ex, ey, ez);
+            if (d2 < best) { best = d2; pos = (int)p; }
+        }
     }
     out_d2 = best;
     out_pos = pos;

@@ -236,9 +236,8 @@ __device__ __noinline__ int shell_continue_nn(const GridView G, const ShellLists
 // best still beyond the listed margin) run the general brick-grid search in place.
 // one scan slot:
 template <int METHOD>
-__device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32& pose, long long i, bool lists) {
+__device__ __forceinline__ void correspond_point(const LinParams& P, const Pose32& pose, long long i, bool lists, float px, float py, float pz) {
     constexpr bool kVoxel = METHOD == PCR_METHOD_VPLANE || METHOD == PCR_METHOD_NDT;
-    const float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
     int pos = -1;
     if (px == px) {                                              // NaN = padding: no match
         float qx, qy, qz, d2;
@@ -259,6 +258,11 @@ __device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32
         if (!settled) pos = general_nn(P.grid, qx, qy, qz, P.max_d2, lists && P.ball_first);
     }
     P.prev[i] = pos;
+}
+
+template <int METHOD>
+__device__ __forceinline__ void correspond_slot(const LinParams& P, const Pose32& pose, long long i, bool lists) {
+    correspond_point<METHOD>(P, pose, i, lists, __ldg(P.sx + i), __ldg(P.sy + i), __ldg(P.sz + i));
 }
 
 // DYNAMIC: warps fetch rows of 32 consecutive scan slots from a device-wide counter (P.grab_rows
@@ -282,7 +286,17 @@ __device__ __forceinline__ void correspond_pass(const LinParams& P, const Pose32
             r0 = __shfl_sync(0xffffffffu, r0, 0);
             if (r0 >= rows_total) break;
             const int r1 = r0 + P.grab_rows < rows_total ? r0 + P.grab_rows : rows_total;
-            for (int r = r0; r < r1; ++r) correspond_slot<METHOD>(P, pose, ((long long)r << 5) + lane, lists);
+            // software pipeline over the rows of one fetch: the next row's coordinates are requested before this row's
+            // list is streamed (the chain scan load -> brick record -> list start -> entries is latency bound)
+            long long i = ((long long)r0 << 5) + lane;
+            float px = __ldg(P.sx + i), py = __ldg(P.sy + i), pz = __ldg(P.sz + i);
+            for (int r = r0; r < r1; ++r) {
+                const long long in = i + 32;
+                float nx = 0.f, ny = 0.f, nz = 0.f;
+                if (r + 1 < r1) { nx = __ldg(P.sx + in); ny = __ldg(P.sy + in); nz = __ldg(P.sz + in); }
+                correspond_point<METHOD>(P, pose, i, lists, px, py, pz);
+                i = in; px = nx; py = ny; pz = nz;
+            }
         }
     } else {
         // static partition of the fused form: the SAME quads of slots the thread accumulates afterwards

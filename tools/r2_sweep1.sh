@@ -16,6 +16,9 @@ except Exception as e:
     print(n, "failed", e, flush=True)
 PY
 }
-run c2_dfma c2 A=1
-run c3_dfma c3 A=1
-run c2i_dfma c2i A=1
+run c2_pipe c2 A=1
+run c3_pipe c3 A=1
+run c4_pipe c4 A=1
+run c2i_pipe c2i A=1
+run c3_pipe_g8 c3 PCR_GRAB_ROWS=8
+run c2_pipe_g4 c2 PCR_GRAB_ROWS=4
