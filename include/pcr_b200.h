@@ -141,6 +141,14 @@ int pcr_sync_producer(pcr_ctx* ctx, int has_stream, void* stream);
  * the record is summed over all ranks before it is returned. */
 int pcr_linearize(pcr_ctx* ctx, int method, const double T[16], double max_dist, double out[PCR_RECORD_LEN]);
 
+/* calc_H_g_e2(cur_T, source) with `source` in HOST memory, as one call: pcr_set_scan_posed + pcr_linearize
+ * with the host->device copy cut into chunks that overlap the ordering and the kernels of the chunk before
+ * (the end-to-end step is bound by that copy).  The scan becomes the resident scan, as after pcr_set_scan_posed.
+ * Small scans, device pointers, multi-GPU contexts and the tile-stream path take the two calls internally.
+ * Replaces the same reference lines as pcr_linearize. */
+int pcr_linearize_host(pcr_ctx* ctx, int method, const double T[16], double max_dist, const float* xyz, int64_t n, int sort,
+                       double out[PCR_RECORD_LEN]);
+
 /* Whole Gauss-Newton solve on the device: linearise, 6x6 solve, stop test BEFORE the update
  * (quirk Q8), T <- T [+] dx, without a host round trip per iteration.  Replaces
  * Registration.align (registration.py:71-113).  `e2_trace` (may be NULL) receives the squared

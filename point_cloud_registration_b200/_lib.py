@@ -43,6 +43,7 @@ SYMBOLS = {
     "pcr_set_scan": (_i, [_vp, _vp, _i64, _i]),
     "pcr_set_scan_posed": (_i, [_vp, _vp, _i64, _i, _vp, _i]),
     "pcr_linearize": (_i, [_vp, _i, _vp, _d, _vp]),
+    "pcr_linearize_host": (_i, [_vp, _i, _vp, _d, _vp, _i64, _i, _vp]),
     "pcr_align": (_i, [_vp, _i, _vp, _i, _d, _d, _vp, _pi, _vp]),
     "pcr_loop_begin": (_i, [_vp, _vp]),
     "pcr_loop_step_async": (_i, [_vp, _i, _i, _d, _d, _i]),
@@ -325,6 +326,15 @@ class Context:
         T = np.ascontiguousarray(T, dtype=np.float64)
         out = np.empty(RECORD_LEN)
         self._check(self._lib.pcr_linearize(self._h, int(method), _ptr(T), float(max_dist), _ptr(out)))
+        return out
+
+    def linearize_host(self, method, T, max_dist, pts_f32, sort=True):
+        """One linearisation of a HOST scan in one call (copy chunks overlap the kernels); the scan becomes
+        the resident scan."""
+        T = np.ascontiguousarray(T, dtype=np.float64)
+        out = np.empty(RECORD_LEN)
+        self._check(self._lib.pcr_linearize_host(self._h, int(method), _ptr(T), float(max_dist), _ptr(pts_f32), pts_f32.shape[0],
+                                                 int(sort), _ptr(out)))
         return out
 
     def linearize_async(self, method, T, max_dist, reps=1):

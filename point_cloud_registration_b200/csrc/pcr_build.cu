@@ -1438,6 +1438,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_TILE_G")) ctx->tile_groups = (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8) ? atoi(e) : 1;
     if (const char* e = getenv("PCR_ACC_MINB")) ctx->acc_min_blocks = atoi(e) == 3 ? 3 : 2;
     if (const char* e = getenv("PCR_TILE_BULK_MIN")) ctx->tile_bulk_min = atoi(e) >= 1 ? atoi(e) : 9;
+    if (const char* e = getenv("PCR_E2E_CHUNKS")) ctx->host_chunks = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 4;
     if (const char* e = getenv("PCR_TILE_SPLIT")) ctx->tile_split = atoi(e) != 0;
     if (const char* e = getenv("PCR_TILE_KR")) ctx->tile_rows_per_unit = atoi(e) == 2 || atoi(e) == 4 ? atoi(e) : 0;
     int rc = ensure_loop_buffers(ctx);
@@ -1466,6 +1467,8 @@ int pcr_destroy(pcr_ctx* ctx) {
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    for (cudaEvent_t e : ctx->ev_chunk) if (e) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return PCR_OK;

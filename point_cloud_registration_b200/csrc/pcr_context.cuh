@@ -168,6 +168,9 @@ struct pcr_ctx {
     double* d_out_mapped = nullptr;      // device alias of h_out
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaEvent_t ev_copy = nullptr;       // host->device scan copy finished (the caller may reuse its buffer)
+    cudaStream_t copy_stream = nullptr;  // pcr_linearize_host: host->device chunks run here while the kernels of the previous chunk run on `stream`
+    cudaEvent_t ev_chunk[8] = {};        // ... one "chunk arrived" event per chunk
+    int host_chunks = 4;                 // chunks of pcr_linearize_host (PCR_E2E_CHUNKS, 1 = no overlap)
     float last_ms = 0.f;
     long long launches = 0;       // kernels launched by this context (all kinds)
 

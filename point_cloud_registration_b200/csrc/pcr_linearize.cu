@@ -556,8 +556,8 @@ int ensure_loop_buffers(pcr_ctx* ctx) {
     PCR_CUDA(cudaMemsetAsync(ctx->state.p, 0, sizeof(LoopState), ctx->stream));
     if (!ctx->h_state) PCR_CUDA(cudaHostAlloc((void**)&ctx->h_state, sizeof(LoopState), cudaHostAllocDefault));
     if (!ctx->h_out) {
-        PCR_CUDA(cudaHostAlloc((void**)&ctx->h_out, 64 * sizeof(double), cudaHostAllocMapped));
-        memset(ctx->h_out, 0, 64 * sizeof(double));
+        PCR_CUDA(cudaHostAlloc((void**)&ctx->h_out, 64 * 8 * sizeof(double), cudaHostAllocMapped));   // 8 record slots (pcr_linearize_host: one per chunk)
+        memset(ctx->h_out, 0, 64 * 8 * sizeof(double));
         PCR_CUDA(cudaHostGetDevicePointer((void**)&ctx->d_out_mapped, ctx->h_out, 0));
     }
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -869,36 +869,11 @@ static int bits_for_u64(unsigned long long v) {   // number of bits needed to re
     return b < 1 ? 1 : b;
 }
 
-static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, const double* T, int method) {
-    if (!ctx) return PCR_ERR_ARG;
-    if (n < 0 || (n > 0 && !xyz)) return fail(ctx, PCR_ERR_ARG, "pcr_set_scan: bad arguments");
-    if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "pcr_set_scan: point count exceeds 2^31-1");
-    PCR_CUDA(cudaSetDevice(ctx->device));
-    ctx->n_scan = n;
-    ctx->n_scan_pad = (n + 31) / 32 * 32;
-    ctx->scan_set = true;
-    ctx->scan_sorted = false;
-
-    if (n == 0) return PCR_OK;
-    const float* d_xyz;
-    const bool from_host = !is_device_pointer(xyz);
-    if (!from_host) {
-        d_xyz = xyz;
-    } else {
-        PCR_CUDA(ctx->scan_raw.ensure((size_t)n * 12));
-        PCR_CUDA(cudaMemcpyAsync(ctx->scan_raw.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
-        PCR_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
-        d_xyz = ctx->scan_raw.as<float>();
-    }
-    const size_t pad_bytes = (size_t)ctx->n_scan_pad * 4;
-    PCR_CUDA(ctx->scan_x.ensure(pad_bytes));
-    PCR_CUDA(ctx->scan_y.ensure(pad_bytes));
-    PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
-    PCR_CUDA(ctx->scan_prev.ensure(pad_bytes));
-    ctx->prev_which = -1;                       // new scan: parked positions are void
-    PCR_CUDA(ctx->scan_hint.ensure((size_t)ctx->n_scan_pad / 32 * 4));
-    fill_float_kernel<<<(unsigned)((ctx->n_scan_pad / 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_hint.as<float>(), ctx->n_scan_pad / 32, ctx->tile_first_radius);
-    PCR_LAUNCH_CHECK();
+// Order n device points (float[3n]) by the correspondence-grid cell of their posed images (or along a Morton
+// curve when no grid exists yet) and lay them out as NaN-padded SoA at sx / sy / sz (n_pad slots); everything on
+// the context's stream, scratch in the context's tmp buffers.
+static int order_and_layout(pcr_ctx* ctx, const float* d_xyz, long long n, long long n_pad, int sort, const double* T, int method,
+                            float* sx, float* sy, float* sz) {
     const uint32_t* order = nullptr;
     if (sort > 0 && n > 1) {
         // the grid the correspondences will be searched in, if it exists already
@@ -975,13 +950,49 @@ static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, co
             ctx->launches += 4;
             order = v_out;
         }
-        ctx->scan_sorted = true;
     }
-    if (sort < 0) ctx->scan_sorted = true;      // caller promises a spatially coherent order
-    scan_to_soa_kernel<<<(unsigned)((ctx->n_scan_pad + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, order, n, ctx->n_scan_pad,
-                                                                                         ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
-                                                                                         ctx->scan_z.as<float>());
+    scan_to_soa_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, order, n, n_pad,
+                                                                                         sx, sy, sz);
     PCR_LAUNCH_CHECK();
+    return PCR_OK;
+}
+
+static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, const double* T, int method) {
+    if (!ctx) return PCR_ERR_ARG;
+    if (n < 0 || (n > 0 && !xyz)) return fail(ctx, PCR_ERR_ARG, "pcr_set_scan: bad arguments");
+    if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "pcr_set_scan: point count exceeds 2^31-1");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    ctx->n_scan = n;
+    ctx->n_scan_pad = (n + 31) / 32 * 32;
+    ctx->scan_set = true;
+    ctx->scan_sorted = false;
+
+    if (n == 0) return PCR_OK;
+    const float* d_xyz;
+    const bool from_host = !is_device_pointer(xyz);
+    if (!from_host) {
+        d_xyz = xyz;
+    } else {
+        PCR_CUDA(ctx->scan_raw.ensure((size_t)n * 12));
+        PCR_CUDA(cudaMemcpyAsync(ctx->scan_raw.p, xyz, (size_t)n * 12, cudaMemcpyHostToDevice, ctx->stream));
+        PCR_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
+        d_xyz = ctx->scan_raw.as<float>();
+    }
+    const size_t pad_bytes = (size_t)ctx->n_scan_pad * 4;
+    PCR_CUDA(ctx->scan_x.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_y.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_prev.ensure(pad_bytes));
+    ctx->prev_which = -1;                       // new scan: parked positions are void
+    PCR_CUDA(ctx->scan_hint.ensure((size_t)ctx->n_scan_pad / 32 * 4));
+    fill_float_kernel<<<(unsigned)((ctx->n_scan_pad / 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_hint.as<float>(), ctx->n_scan_pad / 32, ctx->tile_first_radius);
+    PCR_LAUNCH_CHECK();
+    {
+        int rc = order_and_layout(ctx, d_xyz, n, ctx->n_scan_pad, sort, T, method, ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
+                                  ctx->scan_z.as<float>());
+        if (rc) return rc;
+    }
+    ctx->scan_sorted = sort != 0 && n > 1;
     // Host source: return as soon as the caller's buffer has been read; sort and re-layout keep
     // running on the stream (every consumer is stream-ordered behind them).  Device source: the
     // caller's array must stay untouched until the re-layout has read it, so wait for the stream.
@@ -1029,6 +1040,103 @@ int pcr_linearize(pcr_ctx* ctx, int method, const double T[16], double max_dist,
         memcpy(out, ctx->h_out, PCR_NEQ * sizeof(double));
     }
     PCR_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    return PCR_OK;
+}
+
+// One linearisation of a scan that lives in HOST memory, as ONE call: the scan is cut into chunks; chunk k+1
+// crosses PCIe on a copy stream while chunk k is ordered, searched and accumulated on the compute stream, each
+// chunk leaving its own 29-double record in mapped pinned memory; the records are summed on the host (they are
+// sums over scan points).  End to end this path is bound by the host->device copy (14.3 MB at C2: 0.28 ms at PCIe
+// 5 speed against 0.19 ms of kernels), so hiding everything else behind the copy is what counts.
+int pcr_linearize_host(pcr_ctx* ctx, int method, const double T[16], double max_dist, const float* xyz, int64_t n, int sort,
+                       double out[PCR_RECORD_LEN]) {
+    if (!ctx || !T || !out) return PCR_ERR_ARG;
+    if (n < 0 || (n > 0 && !xyz)) return fail(ctx, PCR_ERR_ARG, "pcr_linearize_host: bad arguments");
+    PCR_CUDA(cudaSetDevice(ctx->device));
+    // chunks of at least 2M points: below that the dozen launches per chunk (ordering + kernels) cost more than the
+    // overlap saves -- measured at C2 (1.19M points): 1599 it/s in one piece, 1410 / 1030 / 591 in 2 / 4 / 8 chunks; at C3
+    // (10M points) 311 -> 376 it/s with 4 chunks (profiles/r2_notes.md)
+    const int K = (int)std::min<long long>(ctx->host_chunks, n / 2000000);
+    // small scans, device-resident scans, multi-GPU contexts and the tile-stream path take the two-step route
+    if (K <= 1 || ctx->nccl_comm || ctx->use_tile || is_device_pointer(xyz)) {
+        int rc = set_scan_impl(ctx, xyz, n, sort, T, method);
+        if (rc) return rc;
+        return pcr_linearize(ctx, method, T, max_dist, out);
+    }
+    if (n >= (1ll << 31)) return fail(ctx, PCR_ERR_LIMIT, "pcr_linearize_host: point count exceeds 2^31-1");
+    ctx->scan_set = true;                                    // (check_method wants a scan; the chunks below become the resident scan)
+    int rc = check_method(ctx, method);
+    if (rc) { ctx->scan_set = false; return rc; }
+    if (!ctx->copy_stream) PCR_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < K; ++k)
+        if (!ctx->ev_chunk[k]) PCR_CUDA(cudaEventCreateWithFlags(&ctx->ev_chunk[k], cudaEventDisableTiming));
+    const long long chunk = ((n + K - 1) / K + 31) / 32 * 32;              // scan points per chunk (the last one may be shorter)
+    const long long n_pad = chunk * (K - 1) + ((n - chunk * (K - 1)) + 31) / 32 * 32;
+    ctx->n_scan = n;
+    ctx->n_scan_pad = n_pad;
+    ctx->scan_sorted = sort != 0;
+    PCR_CUDA(ctx->scan_raw.ensure((size_t)n * 12));
+    const size_t pad_bytes = (size_t)n_pad * 4;
+    PCR_CUDA(ctx->scan_x.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_y.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_z.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_prev.ensure(pad_bytes));
+    PCR_CUDA(ctx->scan_hint.ensure((size_t)n_pad / 32 * 4));
+    PCR_CUDA(cudaMemsetAsync(ctx->scan_prev.p, 0xFF, pad_bytes, ctx->stream));
+    ctx->prev_which = (method == PCR_ICP || method == PCR_PLANE) ? 0 : 1;
+    ctx->prev_epoch = ctx->prev_which == 0 ? ctx->tgt_grid_epoch : ctx->vox_grid_epoch;
+    if ((method == PCR_ICP || method == PCR_PLANE) && !ctx->shell_tried) {
+        rc = pcr_build_correspondence_lists(ctx);
+        if (rc) return rc;
+    }
+    PCR_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    // the copy stream must not overwrite the staging buffer while an earlier call's re-layout still reads it
+    PCR_CUDA(cudaEventRecord(ctx->ev_copy, ctx->stream));
+    PCR_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_copy, 0));
+    for (int k = 0; k < K; ++k) {
+        const long long off = chunk * k, cn = std::min<long long>(chunk, n - off);
+        PCR_CUDA(cudaMemcpyAsync(ctx->scan_raw.as<float>() + 3 * off, xyz + 3 * off, (size_t)cn * 12, cudaMemcpyHostToDevice, ctx->copy_stream));
+        PCR_CUDA(cudaEventRecord(ctx->ev_chunk[k], ctx->copy_stream));
+    }
+    LinParams P{};
+    fill_params(ctx, method, max_dist, P);
+    memcpy(P.T_param, T, sizeof(double) * 16);
+    P.use_param_T = 1; P.device_loop = 0; P.max_iter = 0; P.tol = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const long long off = chunk * k, cn = std::min<long long>(chunk, n - off), cpad = (cn + 31) / 32 * 32;
+        PCR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
+        float* sx = ctx->scan_x.as<float>() + off; float* sy = ctx->scan_y.as<float>() + off; float* sz = ctx->scan_z.as<float>() + off;
+        rc = order_and_layout(ctx, ctx->scan_raw.as<float>() + 3 * off, cn, cpad, sort, T, method, sx, sy, sz);
+        if (rc) return rc;
+        LinParams Pk = P;
+        Pk.sx = sx; Pk.sy = sy; Pk.sz = sz;
+        Pk.prev = ctx->scan_prev.as<int>() + off;
+        Pk.n_pad = cpad;
+        Pk.out_mapped = ctx->d_out_mapped + 64 * k;
+        {
+            const long long rows = cpad / 32, warps = (long long)ctx->sm_count * 4 * (kLinThreads / 32);
+            long long per = ctx->grab_rows > 0 ? ctx->grab_rows : rows / (warps * 16);
+            Pk.grab_rows = (int)(per < 1 ? 1 : (per > 64 ? 64 : per));
+        }
+        switch (method) {
+            case PCR_ICP: rc = launch_method<PCR_METHOD_ICP>(ctx, Pk); break;
+            case PCR_PLANE: rc = launch_method<PCR_METHOD_PLANE>(ctx, Pk); break;
+            case PCR_VPLANE: rc = launch_method<PCR_METHOD_VPLANE>(ctx, Pk); break;
+            default: rc = launch_method<PCR_METHOD_NDT>(ctx, Pk); break;
+        }
+        if (rc) return rc;
+    }
+    PCR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    PCR_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int i = 0; i < PCR_NEQ; ++i) {
+        double v = 0.0;
+        for (int k = 0; k < K; ++k) v += ctx->h_out[64 * k + i];
+        out[i] = v;
+    }
+    PCR_CUDA(cudaEventElapsedTime(&ctx->last_ms, ctx->ev0, ctx->ev1));
+    // tile-stream halo radii: not used on this path, but keep them defined for a later switch
+    fill_float_kernel<<<(unsigned)((n_pad / 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_hint.as<float>(), n_pad / 32, ctx->tile_first_radius);
+    PCR_LAUNCH_CHECK();
     return PCR_OK;
 }
 

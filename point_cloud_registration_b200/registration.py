@@ -65,6 +65,14 @@ class Registration:
         if not self._is_target_set:
             raise ValueError("Target is not set.")
         if not isinstance(source, UploadedScan):
+            src = _lib.as_f32_points(source, "source")
+            if isinstance(src, np.ndarray) and self._dist is None:
+                # host array: upload and linearise in ONE library call (the copy overlaps the kernels)
+                rec = self._ctx.linearize_host(self.method, np.asarray(cur_T, dtype=np.float64), self.max_dist, src,
+                                               sort=self.sort_scan_on_calc)
+                self._scan_generation += 1
+                H, g, e2, self.last_inliers = _lib.record_to_H_g_e2(rec)
+                return H, g, e2
             self._upload(source, sort=self.sort_scan_on_calc, T=cur_T)
         else:
             self._check_handle(source)
