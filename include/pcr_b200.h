@@ -115,7 +115,10 @@ int pcr_get_voxels(pcr_ctx* ctx, double* mean, double* cov, double* norm, double
  * spatially coherent.  Results are identical up to float64 summation order.  With a host source
  * the call returns once the caller's buffer has been read (the re-layout continues on the
  * context's stream, every later call is ordered behind it).  Replaces
- * `source.astype(np.float32)` (registration.py:83). */
+ * `source.astype(np.float32)` (registration.py:83).
+ * sort == 2: like 1, and the caller vouches that this is the same cloud as the previous upload of this size
+ * (e.g. the same array passed to calc_H_g_e2 in every iteration of a host loop): the permutation of that upload
+ * may be reused instead of being recomputed -- any order yields the same correspondences. */
 int pcr_set_scan(pcr_ctx* ctx, const float* xyz, int64_t n, int sort);
 /* Same, with the pose the iteration will start from and the method (PCR_ICP .. PCR_NDT, or -1)
  * whose correspondence grid is meant: with sort > 0 the scan is ordered by the grid cell its posed

@@ -1438,6 +1438,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_TILE_G")) ctx->tile_groups = (atoi(e) == 1 || atoi(e) == 2 || atoi(e) == 4 || atoi(e) == 8) ? atoi(e) : 1;
     if (const char* e = getenv("PCR_ACC_MINB")) ctx->acc_min_blocks = atoi(e) == 3 ? 3 : 2;
     if (const char* e = getenv("PCR_TILE_BULK_MIN")) ctx->tile_bulk_min = atoi(e) >= 1 ? atoi(e) : 9;
+    if (const char* e = getenv("PCR_ORDER_REUSE")) ctx->order_reuse = atoi(e) != 0;
     if (const char* e = getenv("PCR_E2E_CHUNKS")) ctx->host_chunks = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 4;
     if (const char* e = getenv("PCR_TILE_SPLIT")) ctx->tile_split = atoi(e) != 0;
     if (const char* e = getenv("PCR_TILE_KR")) ctx->tile_rows_per_unit = atoi(e) == 2 || atoi(e) == 4 ? atoi(e) : 0;
@@ -1460,6 +1461,7 @@ int pcr_destroy(pcr_ctx* ctx) {
     ctx->vshell_bricks.release(); ctx->vshell_start.release(); ctx->vshell_pts.release(); ctx->vshell_margin2.release();
     ctx->scan_x.release(); ctx->scan_y.release(); ctx->scan_z.release(); ctx->scan_raw.release(); ctx->scan_prev.release();
     ctx->tile_tgt.release(); ctx->tile_vox.release(); ctx->scan_hint.release(); ctx->tile_scratch.release();
+    ctx->scan_order.release();
     ctx->partials.release(); ctx->state.release();
     ctx->tmp_a.release(); ctx->tmp_b.release(); ctx->tmp_c.release(); ctx->tmp_d.release(); ctx->tmp_e.release(); ctx->cub_tmp.release();
     if (ctx->h_state) cudaFreeHost(ctx->h_state);

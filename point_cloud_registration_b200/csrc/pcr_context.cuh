@@ -159,6 +159,10 @@ struct pcr_ctx {
     int prev_which = -1;          // index the positions refer to (0 target grid, 1 voxel grid, -1 none)
     long long prev_epoch = -1, tgt_grid_epoch = 0, vox_grid_epoch = 0;
     pcr::DevBuf scan_raw;         // staging float[3n]
+    pcr::DevBuf scan_order;       // uint32[n]: permutation of the last ordered scan (reused by uploads with sort = 2)
+    long long order_n = -1, order_epoch = -1;
+    int order_method = -2;
+    int order_reuse = 1;          // PCR_ORDER_REUSE=0: recompute the order on every upload
 
     // ---- reduction / loop state ----
     pcr::DevBuf partials;         // double[kMaxLinBlocks * PCR_NEQ_PAD]

@@ -872,10 +872,19 @@ static int bits_for_u64(unsigned long long v) {   // number of bits needed to re
 // Order n device points (float[3n]) by the correspondence-grid cell of their posed images (or along a Morton
 // curve when no grid exists yet) and lay them out as NaN-padded SoA at sx / sy / sz (n_pad slots); everything on
 // the context's stream, scratch in the context's tmp buffers.
+// sort == 2 (whole-scan uploads only, `keep` = true): the caller vouches that this is the SAME cloud as the previous
+// upload (a Gauss-Newton loop on the host calls calc_H_g_e2 with one array every iteration).  The cell order of the
+// first call stays coherent under the small rigid motions in between, and ANY order gives the same correspondences,
+// so the permutation is kept and the key + radix-sort kernels are skipped while (size, method, target) stay the same.
 static int order_and_layout(pcr_ctx* ctx, const float* d_xyz, long long n, long long n_pad, int sort, const double* T, int method,
-                            float* sx, float* sy, float* sz) {
+                            float* sx, float* sy, float* sz, bool keep = false) {
     const uint32_t* order = nullptr;
-    if (sort > 0 && n > 1) {
+    const long long epoch = ctx->tgt_grid_epoch * 1000003ll + ctx->vox_grid_epoch;
+    const bool cached = keep && sort == 2 && ctx->order_reuse && n > 1 && ctx->order_n == n &&
+                        ctx->order_method == method && ctx->order_epoch == epoch && ctx->scan_order.p != nullptr;
+    if (cached) {
+        order = ctx->scan_order.as<uint32_t>();
+    } else if (sort > 0 && n > 1) {
         // the grid the correspondences will be searched in, if it exists already
         const Grid* g = nullptr;
         Grid tile_as_grid;                          // the row grid of the tile-stream path, described as a GridView for the key kernel
@@ -950,6 +959,11 @@ static int order_and_layout(pcr_ctx* ctx, const float* d_xyz, long long n, long 
             ctx->launches += 4;
             order = v_out;
         }
+        if (keep && ctx->order_reuse) {
+            PCR_CUDA(ctx->scan_order.ensure((size_t)n * 4));
+            PCR_CUDA(cudaMemcpyAsync(ctx->scan_order.p, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            ctx->order_n = n; ctx->order_method = method; ctx->order_epoch = epoch;
+        }
     }
     scan_to_soa_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, order, n, n_pad,
                                                                                          sx, sy, sz);
@@ -989,7 +1003,7 @@ static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, co
     PCR_LAUNCH_CHECK();
     {
         int rc = order_and_layout(ctx, d_xyz, n, ctx->n_scan_pad, sort, T, method, ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
-                                  ctx->scan_z.as<float>());
+                                  ctx->scan_z.as<float>(), true);
         if (rc) return rc;
     }
     ctx->scan_sorted = sort != 0 && n > 1;

@@ -24,6 +24,7 @@ class Registration:
         self._dist = None          # (rank, world_size) once attach_communicator() was called
         self._comm_ctx = None      # context that currently owns the NCCL communicator
         self._scan_generation = 0  # bumped by every upload: older UploadedScan handles are refused
+        self._last_source = None   # the array object calc_H_g_e2 was last called with
         self.scan_is_presharded = False   # multi-GPU: scans passed in are already this rank's tile
         self.sort_scan = True      # Morton-sort the scan on upload in align()
         self.sort_scan_on_calc = os.environ.get("PCR_SORT_ON_CALC", "1") != "0"   # ... and in calc_H_g_e2(T, array)
@@ -67,9 +68,14 @@ class Registration:
         if not isinstance(source, UploadedScan):
             src = _lib.as_f32_points(source, "source")
             if isinstance(src, np.ndarray) and self._dist is None:
-                # host array: upload and linearise in ONE library call (the copy overlaps the kernels)
-                rec = self._ctx.linearize_host(self.method, np.asarray(cur_T, dtype=np.float64), self.max_dist, src,
-                                               sort=self.sort_scan_on_calc)
+                # host array: upload and linearise in ONE library call (large copies overlap the kernels).  The same
+                # array OBJECT as in the previous call (a Gauss-Newton loop on the host): its on-device ordering may
+                # be reused -- the reference to it is kept so that no other array can take its identity meanwhile
+                sort = self.sort_scan_on_calc
+                if sort and source is self._last_source:
+                    sort = 2
+                self._last_source = source
+                rec = self._ctx.linearize_host(self.method, np.asarray(cur_T, dtype=np.float64), self.max_dist, src, sort=sort)
                 self._scan_generation += 1
                 H, g, e2, self.last_inliers = _lib.record_to_H_g_e2(rec)
                 return H, g, e2
@@ -134,6 +140,7 @@ class Registration:
             src = src[lo:hi]
         self._ctx.set_scan(src, sort=sort, T=T, method=self.method)
         self._scan_generation += 1
+        self._last_source = None
 
     def attach_communicator(self, rank, world_size, unique_id):
         """Multi-GPU: this process owns one GPU and one contiguous tile of every scan; the

@@ -1,7 +1,7 @@
 #!/bin/bash
 # round 2 sweep 1: tile-stream tunables on C2 (and one C3/C4 line each)
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "device_resident or api_edges or properties or linearize_10k or reference_fixture or near_planar" > gpurun_out/r2_s1_tests.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "device_resident or api_edges or properties or linearize_10k or reference_fixture or align_10k or scheduling" > gpurun_out/r2_s1_tests.log 2>&1
 tail -2 gpurun_out/r2_s1_tests.log
 run() {  # name, workload, env...
   name=$1; wl=$2; shift 2
@@ -16,9 +16,7 @@ except Exception as e:
     print(n, "failed", e, flush=True)
 PY
 }
-run c2_e2e_k4 c2 A=1
-run c2_e2e_k1 c2 PCR_E2E_CHUNKS=1
-run c2_e2e_k2 c2 PCR_E2E_CHUNKS=2
-run c2_e2e_k8 c2 PCR_E2E_CHUNKS=8
-run c3_e2e_k4 c3 A=1
-run c3_e2e_k8 c3 PCR_E2E_CHUNKS=8
+run c2_reuse c2 A=1
+run c2_noreuse c2 PCR_ORDER_REUSE=0
+run c2i_reuse c2i A=1
+run c3_reuse c3 A=1
