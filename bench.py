@@ -69,6 +69,7 @@ WORKLOADS = {
                desc="PlaneICP k=15, ONE fixed workload: scan tile-sharded over the GPUs, target replicated"),
 }
 MAX_DIST, MAX_ITER, TOL = 2.0, 30, 1e-3
+TILES_PER_RANK = int(os.environ.get("PCR_BENCH_TILES", "16"))   # c5, N > 1: Morton tiles per rank, dealt round-robin
 if os.environ.get("PCR_BENCH_TEST_N"):          # test hook (tests/test_bench_contract.py): shrink every workload
     for _w in WORKLOADS.values():
         _w["n"] = int(os.environ["PCR_BENCH_TEST_N"])
@@ -209,7 +210,8 @@ def time_oracle_steps(o, scan_f32, Ts, steps, warmup):
 def workload_config(wl_name, wl, world, n_target, n_scan, **extra):
     cfg = {"workload": f"{wl_name}: {wl['desc']}", "registration": wl["cls"], **wl["kw"], "scan_points": n_scan,
            "target_points": n_target, "max_dist": MAX_DIST, "tol": TOL, "max_iter": MAX_ITER,
-           "parallelism": f"scan tile-sharded x{world}, target replicated" if world > 1 else "single GPU",
+           "parallelism": (f"scan cut into {world * TILES_PER_RANK} spatial (Morton) tiles dealt round-robin over {world} GPUs, target replicated"
+                           if world > 1 else "single GPU"),
            "l2": "flushed between timed iterations (512 MiB memset outside the event pairs)"}
     cfg.update(extra)
     return cfg
@@ -323,7 +325,7 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, context_only
     import torch
     import point_cloud_registration_b200 as pcr
     from point_cloud_registration_b200 import datasets as ds
-    from point_cloud_registration_b200.distributed import shard_bounds
+    from point_cloud_registration_b200.distributed import interleaved_tiles, shard_bounds
 
     dev = torch.device("cuda", local_rank)
     n_total = wl["n"]
@@ -346,12 +348,15 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, context_only
         so3 = ds.lever_arm_so3((0.01, -0.02, 0.03), radius)
         scan_full = ds.perturb_scan_torch(target_in, so3=so3, seed=wl["scan_seed"])
         scan_full = scan_full[ds.morton_order_torch(scan_full)].contiguous()     # contiguous index ranges = spatial tiles
-        data_note = ("synthetic (urban slab at B-01's surface density, generated on the GPU, scan in Morton order so that every rank's "
-                     "contiguous shard is a spatial tile; the CPU legs use the NumPy generator of the same scene family)")
+        data_note = ("synthetic (urban slab at B-01's surface density, generated on the GPU, scan in Morton order, cut into spatial tiles dealt round-robin to the ranks; the CPU legs use the NumPy generator of the same scene family)")
         torch.cuda.synchronize()
     gen_s = time.perf_counter() - t0
-    lo, hi = shard_bounds(n_total, rank, world)
-    n_local = hi - lo
+    # this rank's part of the scan: Morton tiles dealt round-robin (c5), else one contiguous range
+    tiles = interleaved_tiles(n_total, rank, world, TILES_PER_RANK) if (not on_host and world > 1) else [shard_bounds(n_total, rank, world)]
+    n_local = sum(hi - lo for lo, hi in tiles)
+
+    def local_part(x):
+        return x[tiles[0][0]:tiles[0][1]] if len(tiles) == 1 else torch.cat([x[lo:hi] for lo, hi in tiles])
 
     # ---- set_target (once per target; timed separately, not part of the metric) -------------
     reg = cls(max_iter=MAX_ITER, max_dist=MAX_DIST, tol=TOL, device=local_rank, **wl["kw"])
@@ -363,7 +368,7 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, context_only
         from point_cloud_registration_b200.distributed import attach
         attach(reg)
         reg.scan_is_presharded = True
-    scan_local = scan_full[lo:hi]
+    scan_local = local_part(scan_full)
     pinned = torch.empty((n_local, 3), dtype=torch.float32, pin_memory=True)      # host copy of this rank's tile for the end-to-end leg
     pinned.copy_(torch.as_tensor(scan_local) if on_host else scan_local)
     torch.cuda.synchronize()
@@ -522,7 +527,7 @@ def run_b200(args, wl_name, wl, world, rank, local_rank, dist=None, context_only
         # the section-8d rotation NOT matched to the lever arm ("far start"): the rim moves by many metres, beyond
         # max_dist -- the reference does not converge there either; first iterations only, for the record
         scan_far = ds.perturb_scan_torch(target_in, seed=wl["scan_seed"])
-        scan_far = scan_far[ds.morton_order_torch(scan_far)][lo:hi]
+        scan_far = local_part(scan_far[ds.morton_order_torch(scan_far)])
         reg.upload_scan(scan_far.contiguous(), sort=True)
         f_ms, _, _ = timed_trajectory(torch, ctx, method, T0, 5, 5, 5, ext, flush, barrier)
         f_local = float(f_ms.sum())

@@ -15,6 +15,19 @@ def shard_bounds(n, rank, world_size):
     return lo, lo + base + (1 if rank < extra else 0)
 
 
+def interleaved_tiles(n, rank, world_size, tiles_per_rank=16):
+    """Index ranges [(lo, hi), ...] of a spatially ordered n-point scan owned by ``rank``: the scan is cut into
+    ``world_size * tiles_per_rank`` contiguous tiles dealt round-robin.  Every tile stays a compact region (its
+    queries share list cells), and every rank gets tiles from all over the scene -- the cost of a tile varies with
+    its distance from the rotation centre, and one contiguous range per rank left the rim ranks 30 % behind in the
+    first iterations (profiles/r2_notes.md section C)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    k_total = int(world_size) * max(1, int(tiles_per_rank))
+    tiles = [shard_bounds(n, k, k_total) for k in range(rank, k_total, int(world_size))]
+    return [(lo, hi) for lo, hi in tiles if hi > lo]
+
+
 def exchange_unique_id(make_id, rank, group=None):
     """Rank 0 creates the 128-byte NCCL id with ``make_id()``; every rank returns it."""
     import torch.distributed as dist

@@ -83,3 +83,22 @@ def test_shard_bounds_cover_exactly():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_interleaved_tiles_cover_exactly():
+    """bench c5 / multi-GPU users: round-robin tiles partition the scan, each rank within tiles_per_rank points of
+    the others."""
+    from point_cloud_registration_b200.distributed import interleaved_tiles
+    for n in (0, 1, 7, 1000, 100_000_003):
+        for w in (1, 2, 3, 8):
+            for t in (1, 4, 16):
+                owned = [interleaved_tiles(n, r, w, t) for r in range(w)]
+                flat = sorted(x for o in owned for x in o)
+                assert sum(hi - lo for lo, hi in flat) == n
+                assert all(a[1] == b[0] for a, b in zip(flat, flat[1:]))
+                if flat:
+                    assert flat[0][0] == 0 and flat[-1][1] == n
+                sizes = [sum(hi - lo for lo, hi in o) for o in owned]
+                assert max(sizes) - min(sizes) <= t
+    with pytest.raises(ValueError):
+        interleaved_tiles(10, 2, 2)
