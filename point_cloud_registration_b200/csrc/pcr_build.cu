@@ -1440,6 +1440,7 @@ int pcr_create(int device_id, pcr_ctx** out) {
     if (const char* e = getenv("PCR_TILE_BULK_MIN")) ctx->tile_bulk_min = atoi(e) >= 1 ? atoi(e) : 9;
     if (const char* e = getenv("PCR_ORDER_REUSE")) ctx->order_reuse = atoi(e) != 0;
     if (const char* e = getenv("PCR_E2E_CHUNKS")) ctx->host_chunks = atoi(e) >= 1 && atoi(e) <= 8 ? atoi(e) : 4;
+    if (const char* e = getenv("PCR_E2E_MIN_CHUNK")) ctx->host_chunk_min_reuse = atoll(e) >= 64 ? atoll(e) : 2000000;
     if (const char* e = getenv("PCR_TILE_SPLIT")) ctx->tile_split = atoi(e) != 0;
     if (const char* e = getenv("PCR_TILE_KR")) ctx->tile_rows_per_unit = atoi(e) == 2 || atoi(e) == 4 ? atoi(e) : 0;
     int rc = ensure_loop_buffers(ctx);

@@ -872,18 +872,14 @@ static int bits_for_u64(unsigned long long v) {   // number of bits needed to re
 // Order n device points (float[3n]) by the correspondence-grid cell of their posed images (or along a Morton
 // curve when no grid exists yet) and lay them out as NaN-padded SoA at sx / sy / sz (n_pad slots); everything on
 // the context's stream, scratch in the context's tmp buffers.
-// sort == 2 (whole-scan uploads only, `keep` = true): the caller vouches that this is the SAME cloud as the previous
-// upload (a Gauss-Newton loop on the host calls calc_H_g_e2 with one array every iteration).  The cell order of the
-// first call stays coherent under the small rigid motions in between, and ANY order gives the same correspondences,
-// so the permutation is kept and the key + radix-sort kernels are skipped while (size, method, target) stay the same.
+// kept != nullptr: where the permutation of these n points is remembered (OrderCache below).  kept_valid: it holds
+// the permutation of an earlier upload of the same cloud -- it is used as it is and the key + radix-sort kernels are
+// skipped; otherwise the permutation computed here is stored there.
 static int order_and_layout(pcr_ctx* ctx, const float* d_xyz, long long n, long long n_pad, int sort, const double* T, int method,
-                            float* sx, float* sy, float* sz, bool keep = false) {
+                            float* sx, float* sy, float* sz, uint32_t* kept = nullptr, bool kept_valid = false) {
     const uint32_t* order = nullptr;
-    const long long epoch = ctx->tgt_grid_epoch * 1000003ll + ctx->vox_grid_epoch;
-    const bool cached = keep && sort == 2 && ctx->order_reuse && n > 1 && ctx->order_n == n &&
-                        ctx->order_method == method && ctx->order_epoch == epoch && ctx->scan_order.p != nullptr;
-    if (cached) {
-        order = ctx->scan_order.as<uint32_t>();
+    if (kept && kept_valid && n > 1) {
+        order = kept;
     } else if (sort > 0 && n > 1) {
         // the grid the correspondences will be searched in, if it exists already
         const Grid* g = nullptr;
@@ -959,16 +955,38 @@ static int order_and_layout(pcr_ctx* ctx, const float* d_xyz, long long n, long 
             ctx->launches += 4;
             order = v_out;
         }
-        if (keep && ctx->order_reuse) {
-            PCR_CUDA(ctx->scan_order.ensure((size_t)n * 4));
-            PCR_CUDA(cudaMemcpyAsync(ctx->scan_order.p, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
-            ctx->order_n = n; ctx->order_method = method; ctx->order_epoch = epoch;
-        }
+        if (kept) PCR_CUDA(cudaMemcpyAsync(kept, order, (size_t)n * 4, cudaMemcpyDeviceToDevice, ctx->stream));
     }
     scan_to_soa_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, ctx->stream>>>(d_xyz, order, n, n_pad,
                                                                                          sx, sy, sz);
     PCR_LAUNCH_CHECK();
     return PCR_OK;
+}
+
+// The remembered scan order (pcr_set_scan, sort == 2).  A Gauss-Newton loop on the host calls calc_H_g_e2 with one
+// array every iteration: the cell order of its first upload stays coherent under the small rigid motions in between,
+// and ANY order gives the same correspondences -- so the permutation (one per chunk when the upload is pipelined in
+// `chunks` pieces of `chunk_len` points) is kept while (size, partition, method, target structures) stay the same.
+struct OrderCache {
+    uint32_t* slot = nullptr;    // device memory for the permutation(s); nullptr: nothing is kept
+    bool valid = false;          // it holds the order of the previous upload of this cloud
+    long long n, chunk_len, epoch; int chunks, method;
+};
+static int order_cache_open(pcr_ctx* ctx, long long n, long long n_slots, int chunks, long long chunk_len, int sort, int method, OrderCache& oc) {
+    oc.n = n; oc.chunks = chunks; oc.chunk_len = chunk_len; oc.method = method;
+    oc.epoch = ctx->tgt_grid_epoch * 1000003ll + ctx->vox_grid_epoch;
+    if (!ctx->order_reuse || sort <= 0 || n <= 1) return PCR_OK;
+    oc.valid = sort == 2 && ctx->scan_order.p != nullptr && ctx->order_n == n && ctx->order_chunks == chunks &&
+               ctx->order_chunk_len == chunk_len && ctx->order_method == method && ctx->order_epoch == oc.epoch;
+    if (!oc.valid) ctx->order_n = -1;                       // about to be overwritten: void until order_cache_close
+    PCR_CUDA(ctx->scan_order.ensure((size_t)n_slots * 4));  // (same n: same size, a valid content is never reallocated away)
+    oc.slot = ctx->scan_order.as<uint32_t>();
+    return PCR_OK;
+}
+static void order_cache_close(pcr_ctx* ctx, const OrderCache& oc) {
+    if (!oc.slot || oc.valid) return;
+    ctx->order_n = oc.n; ctx->order_chunks = oc.chunks; ctx->order_chunk_len = oc.chunk_len;
+    ctx->order_method = oc.method; ctx->order_epoch = oc.epoch;
 }
 
 static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, const double* T, int method) {
@@ -1002,9 +1020,13 @@ static int set_scan_impl(pcr_ctx* ctx, const float* xyz, int64_t n, int sort, co
     fill_float_kernel<<<(unsigned)((ctx->n_scan_pad / 32 + 255) / 256), 256, 0, ctx->stream>>>(ctx->scan_hint.as<float>(), ctx->n_scan_pad / 32, ctx->tile_first_radius);
     PCR_LAUNCH_CHECK();
     {
-        int rc = order_and_layout(ctx, d_xyz, n, ctx->n_scan_pad, sort, T, method, ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
-                                  ctx->scan_z.as<float>(), true);
+        OrderCache oc;
+        int rc = order_cache_open(ctx, n, n, 1, n, sort, method, oc);
         if (rc) return rc;
+        rc = order_and_layout(ctx, d_xyz, n, ctx->n_scan_pad, sort, T, method, ctx->scan_x.as<float>(), ctx->scan_y.as<float>(),
+                              ctx->scan_z.as<float>(), oc.slot, oc.valid);
+        if (rc) return rc;
+        order_cache_close(ctx, oc);
     }
     ctx->scan_sorted = sort != 0 && n > 1;
     // Host source: return as soon as the caller's buffer has been read; sort and re-layout keep
@@ -1070,7 +1092,11 @@ int pcr_linearize_host(pcr_ctx* ctx, int method, const double T[16], double max_
     // chunks of at least 2M points: below that the dozen launches per chunk (ordering + kernels) cost more than the
     // overlap saves -- measured at C2 (1.19M points): 1599 it/s in one piece, 1410 / 1030 / 591 in 2 / 4 / 8 chunks; at C3
     // (10M points) 311 -> 376 it/s with 4 chunks (profiles/r2_notes.md)
-    const int K = (int)std::min<long long>(ctx->host_chunks, n / 2000000);
+    int K = (int)std::min<long long>(ctx->host_chunks, n / 2000000);
+    // sort == 2 (the same cloud again, see OrderCache): the orders of the chunks are computed once and kept, a chunk then
+    // costs three launches.  Smaller chunks were tried for this case and lost (C2 in 4 chunks of 300k points: 1387 it/s
+    // against 1815 in one piece), so the threshold is the same 2M points unless PCR_E2E_MIN_CHUNK says otherwise
+    if (sort == 2 && ctx->order_reuse) K = std::max(K, (int)std::min<long long>(ctx->host_chunks, n / ctx->host_chunk_min_reuse));
     // small scans, device-resident scans, multi-GPU contexts and the tile-stream path take the two-step route
     if (K <= 1 || ctx->nccl_comm || ctx->use_tile || is_device_pointer(xyz)) {
         int rc = set_scan_impl(ctx, xyz, n, sort, T, method);
@@ -1116,11 +1142,15 @@ int pcr_linearize_host(pcr_ctx* ctx, int method, const double T[16], double max_
     fill_params(ctx, method, max_dist, P);
     memcpy(P.T_param, T, sizeof(double) * 16);
     P.use_param_T = 1; P.device_loop = 0; P.max_iter = 0; P.tol = 0.0;
+    OrderCache oc;
+    rc = order_cache_open(ctx, n, n_pad, K, chunk, sort, method, oc);
+    if (rc) return rc;
     for (int k = 0; k < K; ++k) {
         const long long off = chunk * k, cn = std::min<long long>(chunk, n - off), cpad = (cn + 31) / 32 * 32;
         PCR_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_chunk[k], 0));
         float* sx = ctx->scan_x.as<float>() + off; float* sy = ctx->scan_y.as<float>() + off; float* sz = ctx->scan_z.as<float>() + off;
-        rc = order_and_layout(ctx, ctx->scan_raw.as<float>() + 3 * off, cn, cpad, sort, T, method, sx, sy, sz);
+        rc = order_and_layout(ctx, ctx->scan_raw.as<float>() + 3 * off, cn, cpad, sort, T, method, sx, sy, sz,
+                              oc.slot ? oc.slot + off : nullptr, oc.valid);
         if (rc) return rc;
         LinParams Pk = P;
         Pk.sx = sx; Pk.sy = sy; Pk.sz = sz;
@@ -1140,6 +1170,7 @@ int pcr_linearize_host(pcr_ctx* ctx, int method, const double T[16], double max_
         }
         if (rc) return rc;
     }
+    order_cache_close(ctx, oc);
     PCR_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
     PCR_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int i = 0; i < PCR_NEQ; ++i) {
