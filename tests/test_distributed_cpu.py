@@ -13,7 +13,7 @@ import torch.multiprocessing as mp
 
 from oracle import pcr_oracle as orc
 from point_cloud_registration_b200 import datasets as ds
-from point_cloud_registration_b200.distributed import allreduce_record_host, exchange_unique_id, shard_bounds
+from point_cloud_registration_b200.distributed import allreduce_record_host, exchange_unique_id, interleaved_tiles, shard_bounds
 
 
 def free_port():
@@ -30,7 +30,7 @@ def record_of(H, g, e2, n):
     return rec
 
 
-def worker(rank, world, port, method, out_dir):
+def worker(rank, world, port, method, out_dir, tiles_per_rank=0):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -40,7 +40,10 @@ def worker(rank, world, port, method, out_dir):
         T = np.eye(4)
         T[:3, 3] = [0.02, -0.01, 0.03]
         lo, hi = shard_bounds(len(scan), rank, world)
-        rec = allreduce_record_host(record_of(*orc.linearize(tg, T, scan[lo:hi])))
+        mine = scan[lo:hi]
+        if tiles_per_rank:                                            # bench c5: spatial tiles dealt round-robin
+            mine = np.concatenate([scan[a:b] for a, b in interleaved_tiles(len(scan), rank, world, tiles_per_rank)])
+        rec = allreduce_record_host(record_of(*orc.linearize(tg, T, mine)))
         uid = exchange_unique_id(lambda: b"x" * 128, rank)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), rec=rec, lo=lo, hi=hi, uid=np.frombuffer(uid, dtype=np.uint8))
     finally:
@@ -64,3 +67,21 @@ def test_sharded_linearisation_matches_full(tmp_path, method):
         assert r["rec"][28] == full[28]                       # inlier counts add up exactly
         assert bytes(r["uid"]) == b"x" * 128                  # the id created on rank 0 reached every rank
     assert np.array_equal(recs[0]["rec"], recs[1]["rec"])     # all ranks solve the same system
+
+
+def test_round_robin_tiles_match_full(tmp_path):
+    """The c5 partition (distributed.interleaved_tiles): every rank linearises its tiles from all over the scan;
+    the reduced record is the record of the full scan."""
+    world, method = 2, orc.PLANE
+    mp.spawn(worker, args=(world, free_port(), method, str(tmp_path), 5), nprocs=world, join=True)
+    target = ds.make_urban_slab(30000, seed=3)
+    scan = ds.perturb_scan(target, seed=4, num_points=20001)
+    tg = orc.build_target(method, target, max_dist=2.0, k=10, voxel_size=1.0)
+    T = np.eye(4)
+    T[:3, 3] = [0.02, -0.01, 0.03]
+    full = record_of(*orc.linearize(tg, T, scan))
+    recs = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    for r in recs:
+        assert np.allclose(r["rec"], full, rtol=1e-6, atol=1e-6 * np.max(np.abs(full)))
+        assert r["rec"][28] == full[28]
+    assert np.array_equal(recs[0]["rec"], recs[1]["rec"])
